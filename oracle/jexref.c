@@ -1,0 +1,588 @@
+/*
+ * oracle/jexref.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C, double precision) of the explicit RHS evaluation of
+ * smarras79/Jexpresso for the CG-SEM, conservation-law (CL), inexact-integration,
+ * ContGal path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library; the product (csrc/) never does.
+ *
+ * Every function cites the reference file:line it follows (paths relative to the
+ * reference repository root).  Arrays arrive in the reference's own memory layout:
+ * Julia column-major, 1-based node ids, element index FASTEST in connijk / metrics /
+ * rhs_el (metric_terms.jl:77, mesh.jl:2175).
+ *
+ * Floating-point contract: this file is compiled with -ffp-contract=off.  The
+ * reference's `@turbo` reductions (LoopVectorization: FMA-contracted, order not
+ * specified by the language) are canonicalised here as sequential fused-multiply-add
+ * chains in ascending summation index; every other expression is evaluated with
+ * separately rounded operations in Julia's left-to-right order.  This canonical order
+ * is what the CUDA kernels reproduce.
+ *
+ * PARITY PINNING: the real reference cannot be executed in this image (no Julia).
+ * The restatement is pinned end-to-end against the reference's golden end state
+ * test/CI-ref/CompEuler/theta/output/var_{1..4}_0.h5 (tests/test_oracle_golden.py,
+ * atol 1e-5 as test/ci_cases.jl:57,73); per-RHS and 3D parity are otherwise unpinned
+ * because the reference holds no such vectors.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "jxpow.h"
+
+#define JXO_EQ_EULER_THETA 0
+#define JXO_EQ_EULER_ENERGY 1
+#define JXO_EQ_ADVDIFF 2
+#define JXO_EQ_SHALLOW_WATER 3
+
+#define BC_SENTINEL 4325789.0
+
+typedef struct {
+    int32_t nsd, ngl, neqs;
+    int32_t eq_id, lpert, lsource, lvisc, pow_mode; /* pow_mode 0: libm pow; 1: jx_pow (shared with the device) */
+    int64_t nelem, npoin;
+    double phys[16];          /* [C0, gamma, g, Rair, cp, cv, pref, gamma-1, advdiff u, v, w, swe g, ...] */
+    const double *visc_coeff; /* [neqs] */
+    const int64_t *connijk;   /* [nelem, ngl, ngl, ngl|1] */
+    const double *coords;     /* [nsd, npoin] */
+    const double *met[10];    /* 3D: dξdx dξdy dξdz dηdx dηdy dηdz dζdx dζdy dζdz Je ; 2D: dξdx dξdy dηdx dηdy Je */
+    const double *dpsi;       /* [ngl, ngl], dpsi[m,i] = L'_m(ξ_i) */
+    const double *omega;      /* [ngl] */
+    const double *Minv;       /* [npoin] */
+    const double *qe;         /* [npoin, neqs+1] */
+    int64_t nfaces_bdy;
+    const int64_t *poin_in_bdy_face; /* 3D [nfb, ngl, ngl] ; 2D poin_in_bdy_edge [neb, ngl] */
+    const double *nx, *ny, *nz;      /* same shape */
+    const int32_t *face_kind;        /* 0: periodic tag (skipped, BCs.jl:621-623); 1: free-slip hook */
+    double xmin, xmax, ymin, ymax, zmin, zmax;
+} jxo_problem;
+
+static inline double eos_pow(const jxo_problem *P, double base, double expo) {
+    return P->pow_mode ? jx_pow(base, expo) : pow(base, expo);
+}
+
+/* Kopriva_functions.jl:34-56 */
+static int AlmostEqual(double a, double b) {
+    const double eps = 0.000001;
+    if ((a == 0) || (b == 0) || (a <= eps) || (b <= eps)) {
+        return fabs(a - b) <= 2 * eps;
+    }
+    return (fabs(a - b) <= eps * fabs(a)) && (fabs(a - b) <= eps * fabs(b));
+}
+
+/* ------------------------------------------------------------------------------------------
+ * user hooks.  q, qe are rows of uaux / qe: q[(ieq)*npoin] strides are resolved by the caller
+ * into small local arrays q[0..neqs], qe[0..neqs] (qe[neqs] = reference pressure slot).
+ * ------------------------------------------------------------------------------------------ */
+
+/* constitutiveLaw.jl:22-24  perfectGasLaw_ρθtoP: C0*(ρ*θ)^γ */
+static inline double perfectGasLaw_rtheta2P(const jxo_problem *P, double rho, double theta) {
+    return P->phys[0] * eos_pow(P, rho * theta, P->phys[1]);
+}
+
+/* problems/CompEuler/3d/user_flux.jl:1-77 (TOTAL :1-37, PERT :39-77) */
+static void user_flux_3d(const jxo_problem *P, double *F, double *G, double *H, const double *q, const double *qe) {
+    if (P->eq_id == JXO_EQ_EULER_THETA) {
+        if (!P->lpert) {
+            double r = q[0], ru = q[1], rv = q[2], rw = q[3], rt = q[4];
+            double th = rt / r, u = ru / r, v = rv / r, w = rw / r;
+            double Pr = perfectGasLaw_rtheta2P(P, r, th);
+            F[0] = ru; F[1] = ru * u + Pr; F[2] = ru * v; F[3] = ru * w; F[4] = rt * u;
+            G[0] = rv; G[1] = rv * u; G[2] = rv * v + Pr; G[3] = rv * w; G[4] = rt * v;
+            H[0] = rw; H[1] = rw * u; H[2] = rw * v; H[3] = rw * w + Pr; H[4] = rt * w;
+        } else {
+            double r = q[0] + qe[0], ru = q[1], rv = q[2], rw = q[3], rt = q[4] + qe[4];
+            double th = rt / r, u = ru / r, v = rv / r, w = rw / r;
+            double Pr = perfectGasLaw_rtheta2P(P, r, th);
+            Pr = Pr - qe[5];
+            F[0] = ru; F[1] = ru * u + Pr; F[2] = rv * u; F[3] = rw * u; F[4] = rt * u;
+            G[0] = rv; G[1] = ru * v; G[2] = rv * v + Pr; G[3] = rw * v; G[4] = rt * v;
+            H[0] = rw; H[1] = ru * w; H[2] = rv * w; H[3] = rw * w + Pr; H[4] = rt * w;
+        }
+    } else if (P->eq_id == JXO_EQ_ADVDIFF) {
+        /* problems/AdvDiff/3d_periodic/user_flux.jl:1-16 : F = u q, G = v q, H = w q, constant wind */
+        F[0] = P->phys[8] * q[0];
+        G[0] = P->phys[9] * q[0];
+        H[0] = P->phys[10] * q[0];
+    }
+}
+
+/* problems/CompEuler/theta/user_flux.jl:1-52 ; kelvinHelmholtzChan2022/user_flux.jl:30-48 ;
+ * AdvDiff/kopriva/user_flux.jl:1-16 ; ShallowWater/SoliWaveIsland/user_flux.jl */
+static void user_flux_2d(const jxo_problem *P, double *F, double *G, const double *q, const double *qe) {
+    if (P->eq_id == JXO_EQ_EULER_THETA) {
+        double r, ru, rv, rt;
+        if (!P->lpert) { r = q[0]; ru = q[1]; rv = q[2]; rt = q[3]; }
+        else { r = q[0] + qe[0]; ru = q[1]; rv = q[2]; rt = q[3] + qe[3]; }
+        double th = rt / r, u = ru / r, v = rv / r;
+        double Pr = perfectGasLaw_rtheta2P(P, r, th);
+        if (P->lpert) Pr = Pr - qe[4];
+        F[0] = ru; F[1] = ru * u + Pr; F[2] = rv * u; F[3] = rt * u;
+        G[0] = rv; G[1] = ru * v; G[2] = rv * v + Pr; G[3] = rt * v;
+    } else if (P->eq_id == JXO_EQ_EULER_ENERGY) {
+        /* kelvinHelmholtzChan2022/user_flux.jl:30-48 (TOTAL) */
+        double gamma = P->phys[1], gm1 = P->phys[7];
+        double r = q[0], ru = q[1], rv = q[2], rE = q[3];
+        double u = ru / r, v = rv / r;
+        double ke = 0.5 * r * (u * u + v * v);
+        double Pr = gm1 * (rE - ke);
+        F[0] = ru; F[1] = ru * u + Pr; F[2] = rv * u; F[3] = u * (ke + gamma * Pr / gm1);
+        G[0] = rv; G[1] = ru * v; G[2] = rv * v + Pr; G[3] = v * (ke + gamma * Pr / gm1);
+    } else if (P->eq_id == JXO_EQ_ADVDIFF) {
+        F[0] = P->phys[8] * q[0];
+        G[0] = P->phys[9] * q[0];
+    }
+    (void)qe;
+}
+
+/* problems/CompEuler/3d/user_source.jl:1-66, problems/CompEuler/theta/user_source.jl:1-49:
+ * S[vertical momentum] = -ρ g with ρ = q[1] for both TOTAL and PERT */
+static void user_source(const jxo_problem *P, double *S, const double *q) {
+    for (int e = 0; e < P->neqs; ++e) S[e] = 0.0;
+    if (P->eq_id == JXO_EQ_EULER_THETA) {
+        double r = q[0];
+        S[P->nsd] = -r * P->phys[2];
+    }
+}
+
+/* problems/CompEuler/3d/user_primitives.jl:1-15, problems/CompEuler/theta/user_primitives.jl:1-13 */
+static void user_primitives(const jxo_problem *P, const double *u, const double *qe, double *up) {
+    int q = P->neqs;
+    if (P->eq_id == JXO_EQ_EULER_THETA) {
+        if (!P->lpert) {
+            up[0] = u[0];
+            for (int e = 1; e < q; ++e) up[e] = u[e] / u[0];
+        } else {
+            up[0] = u[0] + qe[0];
+            for (int e = 1; e < q - 1; ++e) up[e] = u[e] / (u[0] + qe[0]);
+            up[q - 1] = (u[q - 1] + qe[q - 1]) / (u[0] + qe[0]) - qe[q - 1] / qe[0];
+        }
+    } else {
+        for (int e = 0; e < q; ++e) up[e] = u[e];
+    }
+}
+
+/* problems/CompEuler/3d/user_bc.jl:1-32, problems/CompEuler/theta/user_bc.jl:1-33 (free slip) */
+static void user_bc_dirichlet(const jxo_problem *P, const double *q, const double *qe, double nx, double ny, double nz,
+                              double *qbdy) {
+    if (P->nsd == 3) {
+        if (!P->lpert) {
+            double qnl = nx * q[1] + ny * q[2] + nz * q[3];
+            qbdy[1] = (q[1] - qnl * nx);
+            qbdy[2] = (q[2] - qnl * ny);
+            qbdy[3] = (q[3] - qnl * nz);
+        } else {
+            double qnl = nx * (q[1] + qe[1]) + ny * (q[2] + qe[2]) + nz * (q[3] + qe[3]);
+            qbdy[1] = (q[1] + qe[1] - qnl * nx) - qe[1];
+            qbdy[2] = (q[2] + qe[2] - qnl * ny) - qe[2];
+            qbdy[3] = (q[3] + qe[3] - qnl * nz) - qe[3];
+        }
+    } else {
+        if (!P->lpert) {
+            double qnl = nx * q[1] + ny * q[2];
+            qbdy[1] = q[1] - qnl * nx;
+            qbdy[2] = q[2] - qnl * ny;
+        } else {
+            double qnl = nx * (q[1] + qe[1]) + ny * (q[2] + qe[2]);
+            qbdy[1] = (q[1] + qe[1] - qnl * nx) - qe[1];
+            qbdy[2] = (q[2] + qe[2] - qnl * ny) - qe[2];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+#define CONN3(iel, i, j, k) conn[(iel) + E * ((i) + n * ((j) + n * (int64_t)(k)))]
+#define MET3(a, iel, i, j, k) (a)[(iel) + E * ((i) + n * ((j) + n * (int64_t)(k)))]
+#define EL5(a, iel, i, j, k, q) (a)[(iel) + E * ((i) + n * ((j) + n * ((k) + n * (int64_t)(q))))]
+#define LOC4(a, i, j, k, q) (a)[(i) + n * ((j) + n * ((k) + n * (q)))]
+#define DPSI(m, i) dpsi[(m) + n * (i)]
+
+typedef struct {
+    double *uaux;      /* [npoin, neqs+1] */
+    double *rhs_el;    /* [E, n^d, neqs] */
+    double *rhs_diff_xi, *rhs_diff_eta, *rhs_diff_zeta, *rhs_diff_el;
+    double *RHS_visc;  /* [npoin, neqs] */
+    double *F, *G, *H, *S, *uprim; /* [n^d, neqs(+1)] */
+} jxo_work;
+
+size_t jxo_work_doubles(const jxo_problem *P) {
+    size_t n = P->ngl, nd = (P->nsd == 3) ? n * n * n : n * n;
+    size_t el = (size_t)P->nelem * nd * P->neqs;
+    size_t tot = (size_t)P->npoin * (P->neqs + 1) + el;
+    if (P->lvisc) tot += 4 * el + (size_t)P->npoin * P->neqs;
+    tot += 4 * nd * P->neqs + nd * (P->neqs + 1);
+    return tot;
+}
+
+static void carve(const jxo_problem *P, double *mem, jxo_work *W) {
+    size_t n = P->ngl, nd = (P->nsd == 3) ? n * n * n : n * n;
+    size_t el = (size_t)P->nelem * nd * P->neqs;
+    W->uaux = mem; mem += (size_t)P->npoin * (P->neqs + 1);
+    W->rhs_el = mem; mem += el;
+    if (P->lvisc) {
+        W->rhs_diff_xi = mem; mem += el;
+        W->rhs_diff_eta = mem; mem += el;
+        W->rhs_diff_zeta = mem; mem += el;
+        W->rhs_diff_el = mem; mem += el;
+        W->RHS_visc = mem; mem += (size_t)P->npoin * P->neqs;
+    }
+    W->F = mem; mem += nd * P->neqs;
+    W->G = mem; mem += nd * P->neqs;
+    W->H = mem; mem += nd * P->neqs;
+    W->S = mem; mem += nd * P->neqs;
+    W->uprim = mem;
+}
+
+/* rhs.jl:29-47 u2uaux! / uaux2u! */
+static void u2uaux(double *uaux, const double *u, int neqs, int64_t npoin) {
+    for (int i = 0; i < neqs; ++i) memcpy(uaux + (size_t)i * npoin, u + (size_t)i * npoin, sizeof(double) * npoin);
+}
+static void uaux2u(double *u, const double *uaux, int neqs, int64_t npoin) {
+    for (int i = 0; i < neqs; ++i) memcpy(u + (size_t)i * npoin, uaux + (size_t)i * npoin, sizeof(double) * npoin);
+}
+
+/* BCs.jl:610-652 (3D) and :183-280 (2D): build_custom_bcs_dirichlet! */
+static void apply_boundary_conditions_dirichlet(const jxo_problem *P, double *u, double *uaux, double *RHS) {
+    const int n = P->ngl, q = P->neqs;
+    const int64_t N = P->npoin, nf = P->nfaces_bdy;
+    double qbdy[16], ql[16], qel[16];
+    const int nloc = (P->nsd == 3) ? n * n : n;
+    for (int64_t iface = 0; iface < nf; ++iface) {
+        if (P->face_kind[iface] == 0) continue; /* periodic tags */
+        /* 3D loop order: i outer, j inner (BCs.jl:625-626); 2D: k = 1:ngl */
+        for (int a = 0; a < n; ++a) {
+            for (int b = 0; b < ((P->nsd == 3) ? n : 1); ++b) {
+                int64_t off = (P->nsd == 3) ? iface + nf * (a + (int64_t)n * b) : iface + nf * (int64_t)a;
+                for (int e = 0; e < q; ++e) qbdy[e] = BC_SENTINEL;
+                int64_t ip = P->poin_in_bdy_face[off] - 1;
+                for (int e = 0; e < q; ++e) ql[e] = uaux[ip + N * e];
+                for (int e = 0; e <= q; ++e) qel[e] = P->qe[ip + N * e];
+                user_bc_dirichlet(P, ql, qel, P->nx[off], P->ny[off], P->nz ? P->nz[off] : 0.0, qbdy);
+                for (int e = 0; e < q; ++e) {
+                    if (!AlmostEqual(qbdy[e], uaux[ip + N * e]) && !AlmostEqual(qbdy[e], BC_SENTINEL)) {
+                        uaux[ip + N * e] = qbdy[e];
+                        RHS[ip + N * e] = 0.0;
+                    }
+                }
+            }
+        }
+    }
+    (void)nloc;
+    uaux2u(u, uaux, q, N);
+}
+
+/* rhs.jl:854-966 _inviscid_rhs_el_3d! + rhs.jl:1615-1698 _expansion_inviscid! (3D) */
+static void inviscid_rhs_el_3d(const jxo_problem *P, jxo_work *W) {
+    const int n = P->ngl, q = P->neqs;
+    const int64_t E = P->nelem, N = P->npoin;
+    const int64_t *conn = P->connijk;
+    const double *dpsi = P->dpsi, *om = P->omega;
+    double *F = W->F, *G = W->G, *H = W->H, *S = W->S;
+    double ql[16], qel[16], f[16], g[16], h[16], s[16];
+    memset(S, 0, sizeof(double) * n * n * n * q);
+    for (int64_t iel = 0; iel < E; ++iel) {
+        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            int64_t ip = CONN3(iel, i, j, k) - 1;
+            for (int e = 0; e < q; ++e) ql[e] = W->uaux[ip + N * e];
+            for (int e = 0; e <= q; ++e) qel[e] = P->qe[ip + N * e];
+            user_flux_3d(P, f, g, h, ql, qel);
+            for (int e = 0; e < q; ++e) { LOC4(F, i, j, k, e) = f[e]; LOC4(G, i, j, k, e) = g[e]; LOC4(H, i, j, k, e) = h[e]; }
+            if (P->lsource) {
+                user_source(P, s, ql);
+                for (int e = 0; e < q; ++e) LOC4(S, i, j, k, e) = s[e];
+            }
+        }
+        for (int ieq = 0; ieq < q; ++ieq) {
+            for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) {
+                double wjk = om[j] * om[k];
+                for (int i = 0; i < n; ++i) {
+                    double Je = MET3(P->met[9], iel, i, j, k);
+                    double wJ = om[i] * wjk * Je;
+                    double dFdxi = 0, dFdeta = 0, dFdzeta = 0, dGdxi = 0, dGdeta = 0, dGdzeta = 0, dHdxi = 0, dHdeta = 0,
+                           dHdzeta = 0;
+                    for (int m = 0; m < n; ++m) { /* @turbo: canonical sequential FMA chain */
+                        dFdxi = fma(DPSI(m, i), LOC4(F, m, j, k, ieq), dFdxi);
+                        dFdeta = fma(DPSI(m, j), LOC4(F, i, m, k, ieq), dFdeta);
+                        dFdzeta = fma(DPSI(m, k), LOC4(F, i, j, m, ieq), dFdzeta);
+                        dGdxi = fma(DPSI(m, i), LOC4(G, m, j, k, ieq), dGdxi);
+                        dGdeta = fma(DPSI(m, j), LOC4(G, i, m, k, ieq), dGdeta);
+                        dGdzeta = fma(DPSI(m, k), LOC4(G, i, j, m, ieq), dGdzeta);
+                        dHdxi = fma(DPSI(m, i), LOC4(H, m, j, k, ieq), dHdxi);
+                        dHdeta = fma(DPSI(m, j), LOC4(H, i, m, k, ieq), dHdeta);
+                        dHdzeta = fma(DPSI(m, k), LOC4(H, i, j, m, ieq), dHdzeta);
+                    }
+                    double xix = MET3(P->met[0], iel, i, j, k), xiy = MET3(P->met[1], iel, i, j, k), xiz = MET3(P->met[2], iel, i, j, k);
+                    double etx = MET3(P->met[3], iel, i, j, k), ety = MET3(P->met[4], iel, i, j, k), etz = MET3(P->met[5], iel, i, j, k);
+                    double zex = MET3(P->met[6], iel, i, j, k), zey = MET3(P->met[7], iel, i, j, k), zez = MET3(P->met[8], iel, i, j, k);
+                    double dFdx = dFdxi * xix + dFdeta * etx + dFdzeta * zex;
+                    double dGdy = dGdxi * xiy + dGdeta * ety + dGdzeta * zey;
+                    double dHdz = dHdxi * xiz + dHdeta * etz + dHdzeta * zez;
+                    double auxi = wJ * ((dFdx + dGdy + dHdz) - LOC4(S, i, j, k, ieq));
+                    EL5(W->rhs_el, iel, i, j, k, ieq) -= auxi;
+                }
+            }
+        }
+    }
+}
+
+#define CONN2(iel, i, j) conn[(iel) + E * ((i) + n * (int64_t)(j))]
+#define MET2(a, iel, i, j) (a)[(iel) + E * ((i) + n * (int64_t)(j))]
+#define EL4(a, iel, i, j, q) (a)[(iel) + E * ((i) + n * ((j) + n * (int64_t)(q)))]
+#define LOC3(a, i, j, q) (a)[(i) + n * ((j) + n * (q))]
+
+/* rhs.jl:763-852 inviscid_rhs_el! (2D, lkep=false) + rhs.jl:1501-1542 _expansion_inviscid! (2D) */
+static void inviscid_rhs_el_2d(const jxo_problem *P, jxo_work *W) {
+    const int n = P->ngl, q = P->neqs;
+    const int64_t E = P->nelem, N = P->npoin;
+    const int64_t *conn = P->connijk;
+    const double *dpsi = P->dpsi, *om = P->omega;
+    double *F = W->F, *G = W->G, *S = W->S;
+    double ql[16], qel[16], f[16], g[16], s[16];
+    memset(S, 0, sizeof(double) * n * n * q);
+    for (int64_t iel = 0; iel < E; ++iel) {
+        for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            int64_t ip = CONN2(iel, i, j) - 1;
+            for (int e = 0; e < q; ++e) ql[e] = W->uaux[ip + N * e];
+            for (int e = 0; e <= q; ++e) qel[e] = P->qe[ip + N * e];
+            user_flux_2d(P, f, g, ql, qel);
+            for (int e = 0; e < q; ++e) { LOC3(F, i, j, e) = f[e]; LOC3(G, i, j, e) = g[e]; }
+            if (P->lsource) {
+                user_source(P, s, ql);
+                for (int e = 0; e < q; ++e) LOC3(S, i, j, e) = s[e];
+            }
+        }
+        for (int ieq = 0; ieq < q; ++ieq) for (int j = 0; j < n; ++j) {
+            double wj = om[j];
+            for (int i = 0; i < n; ++i) {
+                double Je = MET2(P->met[4], iel, i, j);
+                double wJ = om[i] * wj * Je;
+                double dFdxi = 0, dFdeta = 0, dGdxi = 0, dGdeta = 0;
+                for (int k = 0; k < n; ++k) {
+                    dFdxi = fma(DPSI(k, i), LOC3(F, k, j, ieq), dFdxi);
+                    dFdeta = fma(DPSI(k, j), LOC3(F, i, k, ieq), dFdeta);
+                    dGdxi = fma(DPSI(k, i), LOC3(G, k, j, ieq), dGdxi);
+                    dGdeta = fma(DPSI(k, j), LOC3(G, i, k, ieq), dGdeta);
+                }
+                double xix = MET2(P->met[0], iel, i, j), xiy = MET2(P->met[1], iel, i, j);
+                double etx = MET2(P->met[2], iel, i, j), ety = MET2(P->met[3], iel, i, j);
+                double dFdx = dFdxi * xix + dFdeta * etx;
+                double dGdy = dGdxi * xiy + dGdeta * ety;
+                EL4(W->rhs_el, iel, i, j, ieq) -= wJ * ((dFdx + dGdy) - LOC3(S, i, j, ieq));
+            }
+        }
+    }
+}
+
+/* element_matrices.jl:903-918 (3D) / :887-900 (2D) DSS_rhs!: loop order ieq -> iel -> k -> j -> i */
+static void DSS_rhs(const jxo_problem *P, double *RHS, const double *rhs_el) {
+    const int n = P->ngl, q = P->neqs;
+    const int64_t E = P->nelem, N = P->npoin;
+    const int64_t nd = (P->nsd == 3) ? (int64_t)n * n * n : (int64_t)n * n;
+    for (int ieq = 0; ieq < q; ++ieq)
+        for (int64_t iel = 0; iel < E; ++iel)
+            for (int64_t l = 0; l < nd; ++l) {
+                int64_t I = P->connijk[iel + E * l] - 1;
+                RHS[I + N * ieq] += rhs_el[iel + E * (l + nd * ieq)];
+            }
+}
+
+/* rhs.jl:1374-1461 _viscous_rhs_el_3d! + rhs.jl:2794-2867 _expansion_visc! (sgs === nothing, AV) */
+static void viscous_rhs_el_3d(const jxo_problem *P, jxo_work *W) {
+    const int n = P->ngl, q = P->neqs;
+    const int64_t E = P->nelem, N = P->npoin;
+    const int64_t *conn = P->connijk;
+    const double *dpsi = P->dpsi, *om = P->omega;
+    double *U = W->uprim;
+    double ql[16], qel[16], up[16];
+    for (int64_t iel = 0; iel < E; ++iel) {
+        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            int64_t ip = CONN3(iel, i, j, k) - 1;
+            for (int e = 0; e < q; ++e) ql[e] = W->uaux[ip + N * e];
+            for (int e = 0; e <= q; ++e) qel[e] = P->qe[ip + N * e];
+            user_primitives(P, ql, qel, up);
+            for (int e = 0; e < q; ++e) LOC4(U, i, j, k, e) = up[e];
+        }
+        for (int ieq = 0; ieq < q; ++ieq) {
+            const double mu = P->visc_coeff[ieq];
+            for (int m = 0; m < n; ++m) for (int l = 0; l < n; ++l) {
+                double wlm = om[l] * om[m];
+                for (int k = 0; k < n; ++k) {
+                    double Je = MET3(P->met[9], iel, k, l, m);
+                    double wJ = om[k] * wlm * Je;
+                    double dqdxi = 0, dqdeta = 0, dqdzeta = 0;
+                    for (int ii = 0; ii < n; ++ii) {
+                        dqdxi = fma(DPSI(ii, k), LOC4(U, ii, l, m, ieq), dqdxi);
+                        dqdeta = fma(DPSI(ii, l), LOC4(U, k, ii, m, ieq), dqdeta);
+                        dqdzeta = fma(DPSI(ii, m), LOC4(U, k, l, ii, ieq), dqdzeta);
+                    }
+                    double xix = MET3(P->met[0], iel, k, l, m), xiy = MET3(P->met[1], iel, k, l, m), xiz = MET3(P->met[2], iel, k, l, m);
+                    double etx = MET3(P->met[3], iel, k, l, m), ety = MET3(P->met[4], iel, k, l, m), etz = MET3(P->met[5], iel, k, l, m);
+                    double zex = MET3(P->met[6], iel, k, l, m), zey = MET3(P->met[7], iel, k, l, m), zez = MET3(P->met[8], iel, k, l, m);
+                    double auxi = dqdxi * xix + dqdeta * etx + dqdzeta * zex;
+                    double dqdx = mu * auxi;
+                    auxi = dqdxi * xiy + dqdeta * ety + dqdzeta * zey;
+                    double dqdy = mu * auxi;
+                    auxi = dqdxi * xiz + dqdeta * etz + dqdzeta * zez;
+                    double dqdz = mu * auxi;
+                    double gxi = (xix * dqdx + xiy * dqdy + xiz * dqdz) * wJ;
+                    double geta = (etx * dqdx + ety * dqdy + etz * dqdz) * wJ;
+                    double gzeta = (zex * dqdx + zey * dqdy + zez * dqdz) * wJ;
+                    for (int i = 0; i < n; ++i) { /* @turbo: x -= a*b as one fused negated multiply-add */
+                        EL5(W->rhs_diff_xi, iel, i, l, m, ieq) = fma(-DPSI(i, k), gxi, EL5(W->rhs_diff_xi, iel, i, l, m, ieq));
+                        EL5(W->rhs_diff_eta, iel, k, i, m, ieq) = fma(-DPSI(i, l), geta, EL5(W->rhs_diff_eta, iel, k, i, m, ieq));
+                        EL5(W->rhs_diff_zeta, iel, k, l, i, ieq) = fma(-DPSI(i, m), gzeta, EL5(W->rhs_diff_zeta, iel, k, l, i, ieq));
+                    }
+                }
+            }
+        }
+    }
+    size_t tot = (size_t)E * n * n * n * q;
+    for (size_t t = 0; t < tot; ++t) W->rhs_diff_el[t] = W->rhs_diff_xi[t] + W->rhs_diff_eta[t] + W->rhs_diff_zeta[t];
+}
+
+/* rhs.jl:1255-1330 _viscous_rhs_el_2d! + rhs.jl:1973-2056 _expansion_visc! (AV, 2D) */
+static void viscous_rhs_el_2d(const jxo_problem *P, jxo_work *W) {
+    const int n = P->ngl, q = P->neqs;
+    const int64_t E = P->nelem, N = P->npoin;
+    const int64_t *conn = P->connijk;
+    const double *dpsi = P->dpsi, *om = P->omega;
+    double *U = W->uprim;
+    double ql[16], qel[16], up[16];
+    for (int64_t iel = 0; iel < E; ++iel) {
+        for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            int64_t ip = CONN2(iel, i, j) - 1;
+            for (int e = 0; e < q; ++e) ql[e] = W->uaux[ip + N * e];
+            for (int e = 0; e <= q; ++e) qel[e] = P->qe[ip + N * e];
+            user_primitives(P, ql, qel, up);
+            for (int e = 0; e < q; ++e) LOC3(U, i, j, e) = up[e];
+        }
+        for (int ieq = 0; ieq < q; ++ieq) {
+            const double mu = P->visc_coeff[ieq];
+            /* the τ·u augmentation (rhs.jl:1988, 2018-2041) applies only to total-energy runs */
+            const int add_tau_u = (ieq == 3) && (P->eq_id == JXO_EQ_EULER_ENERGY);
+            for (int l = 0; l < n; ++l) {
+                double wl = om[l];
+                for (int k = 0; k < n; ++k) {
+                    double Je = MET2(P->met[4], iel, k, l);
+                    double wJ = om[k] * wl * Je;
+                    double dqdxi = 0, dqdeta = 0;
+                    for (int ii = 0; ii < n; ++ii) {
+                        dqdxi = fma(DPSI(ii, k), LOC3(U, ii, l, ieq), dqdxi);
+                        dqdeta = fma(DPSI(ii, l), LOC3(U, k, ii, ieq), dqdeta);
+                    }
+                    double xix = MET2(P->met[0], iel, k, l), xiy = MET2(P->met[1], iel, k, l);
+                    double etx = MET2(P->met[2], iel, k, l), ety = MET2(P->met[3], iel, k, l);
+                    double auxi = dqdxi * xix + dqdeta * etx;
+                    double dqdx = mu * auxi;
+                    auxi = dqdxi * xiy + dqdeta * ety;
+                    double dqdy = mu * auxi;
+                    double flux_x = dqdx, flux_y = dqdy;
+                    if (add_tau_u) {
+                        double dudxi = 0, dudeta = 0, dvdxi = 0, dvdeta = 0;
+                        for (int ii = 0; ii < n; ++ii) {
+                            dudxi = fma(DPSI(ii, k), LOC3(U, ii, l, 1), dudxi);
+                            dudeta = fma(DPSI(ii, l), LOC3(U, k, ii, 1), dudeta);
+                            dvdxi = fma(DPSI(ii, k), LOC3(U, ii, l, 2), dvdxi);
+                            dvdeta = fma(DPSI(ii, l), LOC3(U, k, ii, 2), dvdeta);
+                        }
+                        double dudx = dudxi * xix + dudeta * etx, dudy = dudxi * xiy + dudeta * ety;
+                        double dvdx = dvdxi * xix + dvdeta * etx, dvdy = dvdxi * xiy + dvdeta * ety;
+                        double div_u = dudx + dvdy;
+                        double mu2 = P->visc_coeff[1];
+                        double txx = 2.0 * mu2 * dudx - (2.0 / 3.0) * mu2 * div_u;
+                        double tyy = 2.0 * mu2 * dvdy - (2.0 / 3.0) * mu2 * div_u;
+                        double txy = mu2 * (dudy + dvdx);
+                        double ul = LOC3(U, k, l, 1), vl = LOC3(U, k, l, 2);
+                        flux_x += txx * ul + txy * vl;
+                        flux_y += txy * ul + tyy * vl;
+                    }
+                    double gxi = (xix * flux_x + xiy * flux_y) * wJ;
+                    double geta = (etx * flux_x + ety * flux_y) * wJ;
+                    for (int i = 0; i < n; ++i) {
+                        EL4(W->rhs_diff_xi, iel, i, l, ieq) = fma(-DPSI(i, k), gxi, EL4(W->rhs_diff_xi, iel, i, l, ieq));
+                        EL4(W->rhs_diff_eta, iel, k, i, ieq) = fma(-DPSI(i, l), geta, EL4(W->rhs_diff_eta, iel, k, i, ieq));
+                    }
+                }
+            }
+        }
+    }
+    size_t tot = (size_t)E * n * n * q;
+    for (size_t t = 0; t < tot; ++t) W->rhs_diff_el[t] = W->rhs_diff_xi[t] + W->rhs_diff_eta[t];
+}
+
+/*
+ * rhs.jl:498-690  _build_rhs!  steps 1-11 (everything up to, not including, DSS_global_RHS!):
+ * zero-fill, u2uaux!, Dirichlet BC (mutates u), inviscid element loop, local DSS, AV viscous
+ * element loop, its DSS and RHS .+= RHS_visc.  `work` has jxo_work_doubles(P) doubles.
+ */
+void jxo_build_rhs_local(const jxo_problem *P, double *u, double *RHS, double time, double *work) {
+    jxo_work W;
+    memset(&W, 0, sizeof(W));
+    carve(P, work, &W);
+    const int q = P->neqs;
+    const int64_t N = P->npoin;
+    const int n = P->ngl;
+    const size_t nd = (P->nsd == 3) ? (size_t)n * n * n : (size_t)n * n;
+    const size_t el = (size_t)P->nelem * nd * q;
+    (void)time;
+    /* resetRHSToZero_inviscid! rhs.jl:68-71 */
+    memset(W.rhs_el, 0, sizeof(double) * el);
+    memset(RHS, 0, sizeof(double) * N * q);
+    /* NOTE uaux column neqs+1 is never written by u2uaux! (rhs.jl:29-35); hooks do not read it */
+    memset(W.uaux + (size_t)N * q, 0, sizeof(double) * N);
+    u2uaux(W.uaux, u, q, N);                                        /* rhs.jl:542 */
+    apply_boundary_conditions_dirichlet(P, u, W.uaux, RHS);         /* rhs.jl:558 */
+    if (P->nsd == 3) {
+        u2uaux(W.uaux, u, q, N);                                    /* rhs.jl:860 */
+        inviscid_rhs_el_3d(P, &W);                                  /* rhs.jl:611 */
+    } else {
+        inviscid_rhs_el_2d(P, &W);
+    }
+    DSS_rhs(P, RHS, W.rhs_el);                                      /* rhs.jl:624 */
+    if (P->lvisc) {
+        /* resetRHSToZero_viscous! rhs.jl:89-102 */
+        memset(W.rhs_diff_xi, 0, sizeof(double) * el);
+        memset(W.rhs_diff_eta, 0, sizeof(double) * el);
+        if (P->nsd == 3) memset(W.rhs_diff_zeta, 0, sizeof(double) * el);
+        memset(W.rhs_diff_el, 0, sizeof(double) * el);
+        memset(W.RHS_visc, 0, sizeof(double) * N * q);
+        if (P->nsd == 3) viscous_rhs_el_3d(P, &W); else viscous_rhs_el_2d(P, &W);   /* rhs.jl:659 */
+        DSS_rhs(P, W.RHS_visc, W.rhs_diff_el);                      /* rhs.jl:671 */
+        for (size_t t = 0; t < (size_t)N * q; ++t) RHS[t] = RHS[t] + W.RHS_visc[t];   /* rhs.jl:672 */
+    }
+}
+
+/* element_matrices.jl:972-978 divide_by_mass_matrix! for every equation (rhs.jl:698-699) */
+void jxo_divide_by_mass_matrix(const jxo_problem *P, double *RHS) {
+    const int64_t N = P->npoin;
+    for (int ieq = 0; ieq < P->neqs; ++ieq)
+        for (int64_t ip = 0; ip < N; ++ip) RHS[ip + N * ieq] = P->Minv[ip] * RHS[ip + N * ieq];
+}
+
+/* rhs.jl:121-134 rhs! for a single rank without inter-rank assembly (g_dss_cache trivial):
+ * du[(i-1)*npoin + j] = RHS[j,i]  -- RHS already has that layout. */
+void jxo_rhs_single(const jxo_problem *P, double *u, double *du, double time, double *work) {
+    jxo_build_rhs_local(P, u, du, time, work);
+    jxo_divide_by_mass_matrix(P, du);
+}
+
+/* assemble_mpi! owner-side add (mpi_communications.jl:292-300): a[idx[i], j] += buf[(i-1)*m + j] */
+void jxo_assemble_add(double *a, int64_t npoin, int m, const int64_t *idx, int64_t len, const double *buf) {
+    for (int j = 0; j < m; ++j)
+        for (int64_t i = 0; i < len; ++i) a[(idx[i] - 1) + npoin * j] = a[(idx[i] - 1) + npoin * j] + buf[i * m + j];
+}
+/* pack (mpi_communications.jl:268-276 and :303-312): buf[(i-1)*m + j] = a[idx[i], j] */
+void jxo_assemble_pack(const double *a, int64_t npoin, int m, const int64_t *idx, int64_t len, double *buf) {
+    for (int j = 0; j < m; ++j)
+        for (int64_t i = 0; i < len; ++i) buf[i * m + j] = a[(idx[i] - 1) + npoin * j];
+}
+/* unpack (mpi_communications.jl:330-337): a[idx[i], j] = buf[(i-1)*m + j] */
+void jxo_assemble_unpack(double *a, int64_t npoin, int m, const int64_t *idx, int64_t len, const double *buf) {
+    for (int j = 0; j < m; ++j)
+        for (int64_t i = 0; i < len; ++i) a[(idx[i] - 1) + npoin * j] = buf[i * m + j];
+}
+
+double jxo_pow(double x, double y, int mode) { return mode ? jx_pow(x, y) : pow(x, y); }
+int jxo_almost_equal(double a, double b) { return AlmostEqual(a, b); }
+size_t jxo_sizeof_problem(void) { return sizeof(jxo_problem); }
