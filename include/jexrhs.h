@@ -1,0 +1,130 @@
+/*
+ * jexrhs.h -- C ABI of libjexrhs, the B200-native (sm_100a, FP64) explicit-RHS engine that
+ * drops in behind Jexpresso's `rhs!(du, u, params, t)` callback.
+ *
+ * The reference has no FFI: its boundary is Julia multiple dispatch
+ *   rhs!(du,u,params,time)                       src/kernel/operators/rhs.jl:121-134
+ *   _build_rhs!(RHS,u,params,time)               src/kernel/operators/rhs.jl:498-711
+ * with `params` built by params_setup (src/kernel/infrastructure/params_setup.jl:442-479).
+ * Each entry point below names the reference interface it replaces.  A Julia host binds
+ * them with `ccall` (julia/rhs_b200.jl); the tests bind them with ctypes.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative JX_E* code; nothing throws across the
+ *    ABI; jx_last_error() returns the message of the last failure on that context;
+ *  - arrays are passed exactly as Julia holds them: column-major, Float64 / Int64, node and
+ *    element ids 1-based; host pointers are borrowed for the duration of the call only;
+ *  - the context owns all device memory (state, metrics, connectivity, M^-1, work arrays stay
+ *    resident in HBM across stages); one context per rank/GPU; not thread-safe;
+ *  - there is NO CPU fallback: without a CUDA device jx_init fails with JX_ENODEV.
+ */
+#ifndef JEXRHS_H
+#define JEXRHS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jx_ctx jx_ctx;
+
+/* error codes */
+#define JX_OK 0
+#define JX_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define JX_ENODEV (-2)   /* no CUDA device */
+#define JX_ECUDA (-3)    /* CUDA runtime error (message in jx_last_error) */
+#define JX_ESTATE (-4)   /* call order violated (e.g. jx_rhs before jx_upload_mesh) */
+#define JX_ENCCL (-5)    /* NCCL error */
+#define JX_ENOMEM (-6)
+
+/* equation sets = registered device functors mirroring the user_flux!/user_source!/
+ * user_primitives!/user_bc_dirichlet! hooks of a case directory (problems/<eqs>/<case>/) */
+#define JX_EQ_EULER_THETA 0    /* problems/CompEuler/3d, problems/CompEuler/theta */
+#define JX_EQ_EULER_ENERGY 1   /* problems/CompEuler/kelvinHelmholtzChan2022 (2D) */
+#define JX_EQ_ADVDIFF 2        /* problems/AdvDiff/kopriva (2D), problems/AdvDiff/3d_periodic */
+#define JX_EQ_SHALLOW_WATER 3  /* problems/ShallowWater/SoliWaveIsland (2D) */
+
+/* stage drivers (OrdinaryDiffEq algorithms used at src/kernel/solvers/TimeIntegrators.jl:597-607) */
+#define JX_SCHEME_CK2N54 0
+#define JX_SCHEME_SSPRK54 1
+#define JX_SCHEME_SSPRK33 2
+
+/* boundary face kinds (src/kernel/boundaryconditions/BCs.jl:621-623) */
+#define JX_BC_SKIP 0           /* periodic* tags: not touched by the Dirichlet loop */
+#define JX_BC_FREE_SLIP 1      /* user_bc_dirichlet! free-slip projection */
+
+/* jx_set_option keys */
+#define JX_OPT_DSS_MODE 1      /* 0 = deterministic gather in the reference's element-ascending
+                                  order (default); 1 = atomics (red.global.add.f64), M^-1 folded */
+#define JX_OPT_POW_MODE 2      /* 0 = CUDA pow() (default); 1 = jx_pow (include/jxpow.h), bit-identical
+                                  to the oracle's jx_pow */
+#define JX_OPT_ELEM_KERNEL 3   /* element-kernel variant, 0 = default */
+
+/* replaces: MPI.Init / get_mpi_comm (src/run.jl:74-88).  nccl_uid: 128-byte ncclUniqueId shared
+ * by all ranks (see jx_nccl_unique_id) or NULL when nranks == 1. */
+int jx_init(int device, int rank, int nranks, const void *nccl_uid, jx_ctx **out);
+int jx_nccl_unique_id(void *uid128);
+void jx_destroy(jx_ctx *);
+int jx_last_error(jx_ctx *, char *buf, int len);
+int jx_set_option(jx_ctx *, int key, int64_t value);
+int jx_version(void);
+
+/* replaces: the scalar part of `params` (params_setup.jl:442-479): SD, neqs, ngl, inputs[:lsource],
+ * inputs[:lvisc], inputs[:SOL_VARS_TYPE] (lpert), visc_coeff = inputs[:μ] (params_setup.jl:307-315),
+ * PhysicalConst (globalConstantsPhysics.jl:3-62) packed as
+ *   phys[0..7] = C0, γ, g, Rair, cp, cv, pref, γ-1 ; phys[8..10] = AdvDiff wind (u,v,w). */
+int jx_set_problem(jx_ctx *, int nsd, int ngl, int neqs, int64_t nelem, int64_t npoin, int equation_id, int lpert,
+                   int lsource, int lvisc, const double *visc_coeff, const double *phys_consts, int nphys);
+
+/* replaces: params.mesh.connijk, params.mesh.coords, params.metrics.{dξdx..dζdz,Je}, params.basis.dψ,
+ * params.ω, params.Minv, params.qp.qe.  metrics: 3D 10 arrays (dξdx dξdy dξdz dηdx dηdy dηdz dζdx dζdy dζdz Je),
+ * 2D 5 arrays (dξdx dξdy dηdx dηdy Je), each Float64[nelem, ngl, ngl, ngl|1] element-fastest. */
+int jx_upload_mesh(jx_ctx *, const int64_t *connijk, const double *coords, const double *const *metrics, int nmetrics,
+                   const double *dpsi, const double *omega, const double *Minv, const double *qe);
+
+/* replaces: params.mesh.poin_in_bdy_face / poin_in_bdy_edge, params.metrics.nx/ny/nz, bdy_face_type
+ * (tags mapped to JX_BC_* kinds by the host).  3D arrays are [nfaces, ngl, ngl], 2D [nedges, ngl]. */
+int jx_upload_bcs(jx_ctx *, int64_t nfaces, const int64_t *poin_in_bdy_face, const double *nx, const double *ny,
+                  const double *nz, const int32_t *face_bc_kind);
+
+/* replaces: AssemblerCache built by setup_assembler (src/kernel/mpi/mpi_communications.jl:48-234).
+ * CSR by peer rank: send_i (local ids sent to owner r), recv_idx (owner-side local ids the values from r add
+ * into), recvback_idx (local ids overwritten with the owner's sum).  Self entries (r == rank) carry the
+ * periodic-twin pairs the reference exchanges by self-send. */
+int jx_upload_halo(jx_ctx *, const int64_t *send_ptr, const int64_t *send_i, const int64_t *recv_ptr,
+                   const int64_t *recv_idx, const int64_t *recvback_ptr, const int64_t *recvback_idx);
+
+/* state: u is the ODE state vector Float64[npoin*neqs], index (ieq-1)*npoin + ip (rhs.jl:29-47) */
+int jx_set_state(jx_ctx *, const double *u);
+int jx_get_state(jx_ctx *, double *u);
+int jx_get_du(jx_ctx *, double *du);
+
+/* replaces: rhs!(du,u,params,time).  u_host != NULL: upload u first; du_host != NULL: download du after.
+ * u_back_host != NULL: download the state after the Dirichlet projection (rhs! mutates u, BCs.jl:651).
+ * All NULL => fully device resident (state set by jx_set_state / advanced by jx_step). */
+int jx_rhs(jx_ctx *, double t, const double *u_host, double *du_host, double *u_back_host);
+
+/* replaces: OrdinaryDiffEq perform_step! for the fixed-step explicit schemes the decks use; all stages on the
+ * device, M^-1 fused with the stage update, no host round trip.  dt is used as given (the Julia side passes
+ * Float64(Float32(Δt)), TimeIntegrators.jl:464-465). */
+int jx_step(jx_ctx *, int scheme, double t, double dt, int nsteps);
+
+/* device-side timing of the last jx_rhs / jx_step call (CUDA events on the context's stream), in ms */
+int jx_last_elapsed_ms(jx_ctx *, float *ms);
+/* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
+int64_t jx_launch_count(jx_ctx *);
+int jx_sync(jx_ctx *);
+
+/* benchmarking helper: `n` device-resident RHS evaluations back to back on the context's stream, timed
+ * with CUDA events.  fused_stage != 0 evaluates a full low-storage RK stage (RHS + M^-1 + stage update with
+ * dt = 0, so the state is unchanged) instead of rhs! alone.  phase_ms (optional, 8 floats) receives the
+ * summed device time per phase: [0] boundary projection, [1] element kernel, [2] DSS gather (or the
+ * zero-fill in atomics mode), [3] interface exchange, [4] M^-1 / stage update passes. */
+int jx_bench_rhs(jx_ctx *, int n, int fused_stage, float *total_ms, float *phase_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JEXRHS_H */

@@ -1,0 +1,859 @@
+// jexrhs.cu -- the C ABI of libjexrhs (include/jexrhs.h): context, uploads, the per-stage RHS
+// pipeline and the fused stage drivers.  Kernels live in jx_kernels.cuh, their instantiations
+// in jx_inst_*.cu.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/jexrhs.h"
+#include "jx_internal.h"
+
+using namespace jx;
+
+// ------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen) so the library loads -- and reports a clear error -- on hosts
+// without NCCL, and shares the copy PyTorch already mapped when both live in one process.
+// ------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm *ncclComm_t;
+struct NcclUid { char internal[128]; };
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(NcclUid *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, NcclUid, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+constexpr int kNcclFloat64 = 8;   // ncclFloat64 / ncclDouble
+
+NcclApi &nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    const char *names[] = {getenv("JX_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        if (!n) continue;
+        api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.h) break;
+    }
+    if (!api.h) return api;
+#define JX_SYM(field, sym) *(void **)(&api.field) = dlsym(api.h, sym)
+    JX_SYM(GetUniqueId, "ncclGetUniqueId");
+    JX_SYM(CommInitRank, "ncclCommInitRank");
+    JX_SYM(CommDestroy, "ncclCommDestroy");
+    JX_SYM(Send, "ncclSend");
+    JX_SYM(Recv, "ncclRecv");
+    JX_SYM(GroupStart, "ncclGroupStart");
+    JX_SYM(GroupEnd, "ncclGroupEnd");
+    JX_SYM(GetErrorString, "ncclGetErrorString");
+#undef JX_SYM
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart &&
+             api.GroupEnd;
+    return api;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+enum { PH_BC = 0, PH_ELEM = 1, PH_DSS = 2, PH_HALO = 3, PH_UPDATE = 4, PH_COUNT = 8 };
+
+struct PeerSeg {
+    int peer;
+    int64_t off, len;     // offset/length (in nodes) inside the concatenated list
+};
+struct AddRound {
+    int64_t off, len;     // range inside d_add_sel (positions into the concatenated recv list)
+};
+
+struct jx_ctx {
+    int device = 0, rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+    std::string err;
+    int num_sms = 148;
+    int64_t launches = 0;
+
+    // problem (jx_set_problem)
+    bool have_problem = false, have_mesh = false;
+    int nsd = 0, ngl = 0, neqs = 0, eq_id = 0, lpert = 0, lsource = 0, lvisc = 0;
+    int64_t nelem = 0, npoin = 0;
+    double visc[8] = {0};
+    Phys phys;
+    const KernelSet *ks = nullptr;
+    int np = 0, nmet = 0, rec_bytes = 0;
+
+    // options
+    int dss_mode = 0, pow_mode = 0, elem_variant = 0;
+
+    // device arrays
+    double *u = nullptr, *du = nullptr, *tmp = nullptr, *qe = nullptr, *Minv = nullptr, *coords = nullptr;
+    double *rhs_el = nullptr, *rhs_el_visc = nullptr;
+    char *rec = nullptr;
+    int64_t *n2e_ptr = nullptr;
+    uint32_t *n2e_idx = nullptr;
+    double dpsi[64] = {0};
+    double *ss[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // SSPRK scratch (uprev, u2, u3, u4, k3)
+
+    // boundary projection lists
+    int nb = 0;
+    int32_t *bc_node = nullptr, *bc_ptr = nullptr;
+    double *bc_normal = nullptr;
+
+    // interface / periodic assembly (AssemblerCache)
+    bool have_halo = false;
+    std::vector<PeerSeg> send_seg, recv_seg;        // by peer, ascending
+    int64_t nsend = 0, nrecv = 0;
+    int64_t *d_send_i = nullptr, *d_recv_idx = nullptr, *d_recvback_idx = nullptr;
+    double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
+    std::vector<std::vector<AddRound>> add_rounds;   // per recv segment: rounds of conflict-free positions
+    int64_t *d_add_sel = nullptr;
+
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    bool phase_timing = false;
+    std::vector<cudaEvent_t> ph_ev;                  // pairs (start, stop) tagged by ph_tag
+    std::vector<int> ph_tag;
+};
+
+namespace {
+
+int fail(jx_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(c, e_ == cudaErrorMemoryAllocation ? JX_ENOMEM : JX_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, \
+                        #call, cudaGetErrorString(e_));                                                   \
+    } while (0)
+
+#define NCK(call)                                                                                               \
+    do {                                                                                                        \
+        int e_ = (call);                                                                                        \
+        if (e_ != 0)                                                                                            \
+            return fail(c, JX_ENCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call,                                 \
+                        nccl().GetErrorString ? nccl().GetErrorString(e_) : "nccl error");                      \
+    } while (0)
+
+template <class T>
+int dalloc(jx_ctx *c, T **p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    CK(cudaMalloc((void **)p, count * sizeof(T)));
+    return JX_OK;
+}
+template <class T>
+void dfree(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+struct PhaseScope {
+    jx_ctx *c;
+    bool on;
+    PhaseScope(jx_ctx *c_, int tag) : c(c_), on(c_->phase_timing) {
+        if (!on) return;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        c->ph_ev.push_back(a);
+        c->ph_ev.push_back(b);
+        c->ph_tag.push_back(tag);
+        cudaEventRecord(a, c->stream);
+    }
+    ~PhaseScope() {
+        if (on) cudaEventRecord(c->ph_ev.back(), c->stream);
+    }
+};
+
+void free_mesh(jx_ctx *c) {
+    dfree(c->u); dfree(c->du); dfree(c->tmp); dfree(c->qe); dfree(c->Minv); dfree(c->coords);
+    dfree(c->rhs_el); dfree(c->rhs_el_visc); dfree(c->rec); dfree(c->n2e_ptr); dfree(c->n2e_idx);
+    for (auto &p : c->ss) dfree(p);
+    c->have_mesh = false;
+}
+void free_bcs(jx_ctx *c) {
+    dfree(c->bc_node); dfree(c->bc_ptr); dfree(c->bc_normal);
+    c->nb = 0;
+}
+void free_halo(jx_ctx *c) {
+    dfree(c->d_send_i); dfree(c->d_recv_idx); dfree(c->d_recvback_idx); dfree(c->d_sendbuf); dfree(c->d_recvbuf);
+    dfree(c->d_add_sel);
+    c->send_seg.clear(); c->recv_seg.clear(); c->add_rounds.clear();
+    c->nsend = c->nrecv = 0;
+    c->have_halo = false;
+}
+
+int select_kernels(jx_ctx *c) {
+    const KernelSet *ks = nullptr;
+    if (c->eq_id == JX_EQ_EULER_THETA && c->nsd == 3)
+        ks = lookup_euler_theta_3d(c->ngl, c->lpert, c->pow_mode, c->lvisc, c->elem_variant);
+    else if (c->eq_id == JX_EQ_EULER_THETA && c->nsd == 2)
+        ks = lookup_euler_theta_2d(c->ngl, c->lpert, c->pow_mode, c->lvisc, c->elem_variant);
+    else
+        ks = lookup_other(c->nsd, c->ngl, c->eq_id, c->lvisc, c->elem_variant);
+    if (!ks)
+        return fail(c, JX_EINVAL, "no kernel for nsd=%d ngl=%d eq=%d lpert=%d pow=%d lvisc=%d variant=%d", c->nsd, c->ngl,
+                    c->eq_id, c->lpert, c->pow_mode, c->lvisc, c->elem_variant);
+    if (ks->neq != c->neqs) return fail(c, JX_EINVAL, "equation set %d has %d equations, got neqs=%d", c->eq_id, ks->neq, c->neqs);
+    CK(ks->prepare());
+    c->ks = ks;
+    return JX_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------
+extern "C" int jx_version(void) { return 100; }
+
+extern "C" int jx_nccl_unique_id(void *uid128) {
+    if (!uid128) return JX_EINVAL;
+    if (!nccl().ok) return JX_ENCCL;
+    NcclUid id;
+    if (nccl().GetUniqueId(&id) != 0) return JX_ENCCL;
+    memcpy(uid128, &id, 128);
+    return JX_OK;
+}
+
+extern "C" int jx_init(int device, int rank, int nranks, const void *nccl_uid, jx_ctx **out) {
+    if (!out) return JX_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return JX_ENODEV;   // no CPU fallback
+    if (device < 0 || device >= ndev || nranks < 1 || rank < 0 || rank >= nranks) return JX_EINVAL;
+    jx_ctx *c = new jx_ctx();
+    c->device = device; c->rank = rank; c->nranks = nranks;
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return JX_ECUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return JX_ECUDA; }
+    c->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return JX_ECUDA; }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    if (nranks > 1) {
+        if (!nccl_uid || !nccl().ok) { jx_destroy(c); return JX_ENCCL; }
+        NcclUid id;
+        memcpy(&id, nccl_uid, 128);
+        if (nccl().CommInitRank(&c->comm, nranks, id, rank) != 0) { jx_destroy(c); return JX_ENCCL; }
+    }
+    *out = c;
+    return JX_OK;
+}
+
+extern "C" void jx_destroy(jx_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_mesh(c); free_bcs(c); free_halo(c);
+    for (auto e : c->ph_ev) cudaEventDestroy(e);
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int jx_last_error(jx_ctx *c, char *buf, int len) {
+    if (!c || !buf || len <= 0) return JX_EINVAL;
+    snprintf(buf, (size_t)len, "%s", c->err.c_str());
+    return JX_OK;
+}
+
+extern "C" int jx_set_option(jx_ctx *c, int key, int64_t value) {
+    if (!c) return JX_EINVAL;
+    switch (key) {
+        case JX_OPT_DSS_MODE:
+            if (value != 0 && value != 1) return fail(c, JX_EINVAL, "dss mode must be 0 or 1");
+            c->dss_mode = (int)value;
+            break;
+        case JX_OPT_POW_MODE:
+            if (value != 0 && value != 1) return fail(c, JX_EINVAL, "pow mode must be 0 or 1");
+            c->pow_mode = (int)value;
+            break;
+        case JX_OPT_ELEM_KERNEL: c->elem_variant = (int)value; break;
+        default: return fail(c, JX_EINVAL, "unknown option %d", key);
+    }
+    if (c->have_problem) return select_kernels(c);
+    return JX_OK;
+}
+
+extern "C" int jx_set_problem(jx_ctx *c, int nsd, int ngl, int neqs, int64_t nelem, int64_t npoin, int equation_id, int lpert,
+                              int lsource, int lvisc, const double *visc_coeff, const double *phys_consts, int nphys) {
+    if (!c) return JX_EINVAL;
+    if ((nsd != 2 && nsd != 3) || ngl < 2 || ngl > 8 || neqs < 1 || neqs > 8 || nelem < 0 || npoin < 0 || nphys < 0 || nphys > 16)
+        return fail(c, JX_EINVAL, "jx_set_problem: bad dimensions");
+    if (npoin >= (int64_t)1 << 31) return fail(c, JX_EINVAL, "npoin must be < 2^31 per rank");
+    cudaSetDevice(c->device);
+    free_mesh(c); free_bcs(c); free_halo(c);
+    c->nsd = nsd; c->ngl = ngl; c->neqs = neqs; c->nelem = nelem; c->npoin = npoin;
+    c->eq_id = equation_id; c->lpert = lpert ? 1 : 0; c->lsource = lsource ? 1 : 0; c->lvisc = lvisc ? 1 : 0;
+    for (int i = 0; i < 8; ++i) c->visc[i] = (visc_coeff && i < neqs) ? visc_coeff[i] : 0.0;
+    for (int i = 0; i < 16; ++i) c->phys.v[i] = (phys_consts && i < nphys) ? phys_consts[i] : 0.0;
+    c->np = 1;
+    for (int d = 0; d < nsd; ++d) c->np *= ngl;
+    c->nmet = nsd * nsd + 1;
+    const int npp = (c->np + 3) / 4 * 4;
+    c->rec_bytes = (c->nmet * c->np * 8 + npp * 4 + 15) / 16 * 16;
+    if ((int64_t)c->np * nelem >= ((int64_t)1 << 32)) return fail(c, JX_EINVAL, "nelem*ngl^nsd must be < 2^32 per rank");
+    c->have_problem = true;
+    return select_kernels(c);
+}
+
+// ------------------------------------------------------------------------------------------
+// uploads
+// ------------------------------------------------------------------------------------------
+extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *coords, const double *const *metrics,
+                              int nmetrics, const double *dpsi, const double *omega, const double *Minv, const double *qe) {
+    if (!c) return JX_EINVAL;
+    if (!c->have_problem) return fail(c, JX_ESTATE, "jx_upload_mesh before jx_set_problem");
+    if (!connijk || !metrics || !dpsi || !omega || !Minv) return fail(c, JX_EINVAL, "jx_upload_mesh: null array");
+    if (nmetrics != c->nmet) return fail(c, JX_EINVAL, "expected %d metric arrays, got %d", c->nmet, nmetrics);
+    cudaSetDevice(c->device);
+    free_mesh(c);
+    const int64_t E = c->nelem, N = c->npoin;
+    const int np = c->np, q = c->neqs;
+    const int64_t total = E * np;
+    const size_t nq = (size_t)N * q;
+    int rc;
+    if ((rc = dalloc(c, &c->u, nq)) || (rc = dalloc(c, &c->du, nq)) || (rc = dalloc(c, &c->tmp, nq)) ||
+        (rc = dalloc(c, &c->Minv, (size_t)N)) || (rc = dalloc(c, &c->qe, (size_t)N * (q + 1))) ||
+        (rc = dalloc(c, &c->coords, (size_t)N * c->nsd)) || (rc = dalloc(c, &c->rec, (size_t)E * c->rec_bytes)) ||
+        (rc = dalloc(c, &c->n2e_ptr, (size_t)N + 1)) || (rc = dalloc(c, &c->n2e_idx, (size_t)total)))
+        return rc;
+    CK(cudaMemsetAsync(c->u, 0, nq * 8, c->stream));
+    CK(cudaMemsetAsync(c->du, 0, nq * 8, c->stream));
+    CK(cudaMemsetAsync(c->tmp, 0, nq * 8, c->stream));
+    CK(cudaMemcpyAsync(c->Minv, Minv, (size_t)N * 8, cudaMemcpyHostToDevice, c->stream));
+    if (qe) CK(cudaMemcpyAsync(c->qe, qe, (size_t)N * (q + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    else CK(cudaMemsetAsync(c->qe, 0, (size_t)N * (q + 1) * 8, c->stream));
+    for (int i = 0; i < c->ngl * c->ngl; ++i) c->dpsi[i] = dpsi[i];
+
+    // staging buffer reused for every element-sized host array
+    double *d_stage = nullptr, *d_omega = nullptr;
+    int64_t *d_conn = nullptr;
+    int32_t *d_cnt = nullptr;
+    if ((rc = dalloc(c, &d_stage, (size_t)std::max<int64_t>(total, N * c->nsd))) || (rc = dalloc(c, &d_omega, (size_t)c->ngl)) ||
+        (rc = dalloc(c, &d_conn, (size_t)total)) || (rc = dalloc(c, &d_cnt, (size_t)N)))
+        return rc;
+    auto cleanup = [&]() { dfree(d_stage); dfree(d_omega); dfree(d_conn); dfree(d_cnt); };
+#define CKC(call)                                                                                    \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            cleanup();                                                                               \
+            return fail(c, JX_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+        }                                                                                            \
+    } while (0)
+    CKC(cudaMemcpyAsync(d_omega, omega, (size_t)c->ngl * 8, cudaMemcpyHostToDevice, c->stream));
+    CKC(cudaMemcpyAsync(d_conn, connijk, (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
+    RetileArgs ra;
+    ra.omega = d_omega; ra.connijk = d_conn; ra.rec = c->rec; ra.nelem = E; ra.nsd = c->nsd; ra.ngl = c->ngl; ra.np = np;
+    ra.nmet = c->nmet; ra.npp = (np + 3) / 4 * 4; ra.rec_bytes = c->rec_bytes; ra.src = nullptr;
+    if (total > 0) {
+        CKC(cudaMemsetAsync(c->rec, 0, (size_t)E * c->rec_bytes, c->stream));
+        ra.slot = -1;
+        k_retile<<<nblk(total, 256), 256, 0, c->stream>>>(ra);
+        for (int m = 0; m < c->nmet; ++m) {
+            if (!metrics[m]) { cleanup(); return fail(c, JX_EINVAL, "metric array %d is null", m); }
+            CKC(cudaMemcpyAsync(d_stage, metrics[m], (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
+            ra.src = d_stage; ra.slot = m;
+            k_retile<<<nblk(total, 256), 256, 0, c->stream>>>(ra);
+            CKC(cudaStreamSynchronize(c->stream));   // host array may be pageable: keep the staging reuse ordered
+        }
+        c->launches += c->nmet + 1;
+    }
+    // coords: Julia [nsd, N] -> device [nsd][N]
+    if (coords && N > 0) {
+        std::vector<double> soa((size_t)N * c->nsd);
+        for (int d = 0; d < c->nsd; ++d)
+            for (int64_t ip = 0; ip < N; ++ip) soa[(size_t)d * N + ip] = coords[(size_t)ip * c->nsd + d];
+        CKC(cudaMemcpy(c->coords, soa.data(), soa.size() * 8, cudaMemcpyHostToDevice));
+    } else {
+        CKC(cudaMemsetAsync(c->coords, 0, (size_t)std::max<int64_t>(1, N * c->nsd) * 8, c->stream));
+    }
+    // node -> (element, local) CSR in DSS_rhs! order (element ascending)
+    {
+        CKC(cudaMemsetAsync(d_cnt, 0, (size_t)std::max<int64_t>(1, N) * 4, c->stream));
+        if (total > 0) k_count_valence<<<nblk(total, 256), 256, 0, c->stream>>>(d_conn, total, d_cnt);
+        std::vector<int32_t> cnt((size_t)N);
+        CKC(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)N * 4, cudaMemcpyDeviceToHost, c->stream));
+        CKC(cudaStreamSynchronize(c->stream));
+        std::vector<int64_t> ptr((size_t)N + 1);
+        ptr[0] = 0;
+        for (int64_t i = 0; i < N; ++i) ptr[i + 1] = ptr[i] + cnt[i];
+        if (ptr[N] != total) { cleanup(); return fail(c, JX_EINVAL, "connijk holds ids outside 1..npoin"); }
+        CKC(cudaMemcpyAsync(c->n2e_ptr, ptr.data(), ((size_t)N + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        CKC(cudaMemsetAsync(d_cnt, 0, (size_t)std::max<int64_t>(1, N) * 4, c->stream));
+        if (total > 0) {
+            k_fill_n2e<<<nblk(total, 256), 256, 0, c->stream>>>(d_conn, E, np, c->n2e_ptr, d_cnt, c->n2e_idx);
+            k_sort_n2e<<<nblk(N, 128), 128, 0, c->stream>>>(N, c->n2e_ptr, c->n2e_idx);
+            c->launches += 3;
+        }
+        CKC(cudaStreamSynchronize(c->stream));
+    }
+    CKC(cudaGetLastError());
+    cleanup();
+#undef CKC
+    c->have_mesh = true;
+    return JX_OK;
+}
+
+extern "C" int jx_upload_bcs(jx_ctx *c, int64_t nfaces, const int64_t *poin_in_bdy_face, const double *nx, const double *ny,
+                             const double *nz, const int32_t *face_bc_kind) {
+    if (!c) return JX_EINVAL;
+    if (!c->have_problem) return fail(c, JX_ESTATE, "jx_upload_bcs before jx_set_problem");
+    cudaSetDevice(c->device);
+    free_bcs(c);
+    if (nfaces <= 0) return JX_OK;
+    if (!poin_in_bdy_face || !nx || !ny || !face_bc_kind || (c->nsd == 3 && !nz)) return fail(c, JX_EINVAL, "jx_upload_bcs: null array");
+    const int n = c->ngl;
+    const int per_face = (c->nsd == 3) ? n * n : n;
+    // hits in the reference's visiting order: face ascending, then i outer / j inner (BCs.jl:621-626)
+    struct Hit { int32_t node; int64_t seq; double nx, ny, nz; };
+    std::vector<Hit> hits;
+    hits.reserve((size_t)nfaces * per_face);
+    int64_t seq = 0;
+    for (int64_t f = 0; f < nfaces; ++f) {
+        if (face_bc_kind[f] == JX_BC_SKIP) continue;
+        if (face_bc_kind[f] != JX_BC_FREE_SLIP) return fail(c, JX_EINVAL, "face %lld: unknown bc kind %d", (long long)f, face_bc_kind[f]);
+        for (int a = 0; a < n; ++a)
+            for (int b = 0; b < (c->nsd == 3 ? n : 1); ++b) {
+                const int64_t off = (c->nsd == 3) ? f + nfaces * (a + (int64_t)n * b) : f + nfaces * (int64_t)a;
+                const int64_t ip = poin_in_bdy_face[off] - 1;
+                if (ip < 0 || ip >= c->npoin) return fail(c, JX_EINVAL, "poin_in_bdy_face holds ids outside 1..npoin");
+                hits.push_back({(int32_t)ip, seq++, nx[off], ny[off], nz ? nz[off] : 0.0});
+            }
+    }
+    std::stable_sort(hits.begin(), hits.end(), [](const Hit &x, const Hit &y) { return x.node < y.node; });
+    std::vector<int32_t> node, ptr;
+    std::vector<double> normal(hits.size() * 3);
+    for (size_t h = 0; h < hits.size(); ++h) {
+        if (h == 0 || hits[h].node != hits[h - 1].node) { node.push_back(hits[h].node); ptr.push_back((int32_t)h); }
+        normal[3 * h] = hits[h].nx; normal[3 * h + 1] = hits[h].ny; normal[3 * h + 2] = hits[h].nz;
+    }
+    ptr.push_back((int32_t)hits.size());
+    c->nb = (int)node.size();
+    if (c->nb == 0) return JX_OK;
+    int rc;
+    if ((rc = dalloc(c, &c->bc_node, node.size())) || (rc = dalloc(c, &c->bc_ptr, ptr.size())) ||
+        (rc = dalloc(c, &c->bc_normal, normal.size())))
+        return rc;
+    CK(cudaMemcpy(c->bc_node, node.data(), node.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->bc_ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->bc_normal, normal.data(), normal.size() * 8, cudaMemcpyHostToDevice));
+    return JX_OK;
+}
+
+extern "C" int jx_upload_halo(jx_ctx *c, const int64_t *send_ptr, const int64_t *send_i, const int64_t *recv_ptr,
+                              const int64_t *recv_idx, const int64_t *recvback_ptr, const int64_t *recvback_idx) {
+    if (!c) return JX_EINVAL;
+    if (!c->have_problem) return fail(c, JX_ESTATE, "jx_upload_halo before jx_set_problem");
+    cudaSetDevice(c->device);
+    free_halo(c);
+    if (!send_ptr || !recv_ptr || !recvback_ptr) return fail(c, JX_EINVAL, "jx_upload_halo: null pointer array");
+    const int R = c->nranks;
+    const int64_t ns = send_ptr[R], nr = recv_ptr[R];
+    if (recvback_ptr[R] != ns) return fail(c, JX_EINVAL, "recvback lists must mirror the send lists");
+    for (int r = 0; r < R; ++r) {
+        if (send_ptr[r + 1] - send_ptr[r] != recvback_ptr[r + 1] - recvback_ptr[r])
+            return fail(c, JX_EINVAL, "recvback list of peer %d differs in length from the send list", r);
+        if (send_ptr[r + 1] > send_ptr[r]) c->send_seg.push_back({r, send_ptr[r], send_ptr[r + 1] - send_ptr[r]});
+        if (recv_ptr[r + 1] > recv_ptr[r]) c->recv_seg.push_back({r, recv_ptr[r], recv_ptr[r + 1] - recv_ptr[r]});
+    }
+    const int64_t self_s = send_ptr[c->rank + 1] - send_ptr[c->rank], self_r = recv_ptr[c->rank + 1] - recv_ptr[c->rank];
+    if (self_s != self_r) return fail(c, JX_EINVAL, "self send/recv lists differ in length");
+    if (ns == 0 && nr == 0) return JX_OK;
+    if (R > 1 && !c->comm && (ns != self_s || nr != self_r)) return fail(c, JX_ENCCL, "remote peers listed but no communicator");
+    auto to0 = [&](const int64_t *src, int64_t n, std::vector<int64_t> &dst) -> bool {
+        dst.resize((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            dst[i] = src[i] - 1;
+            if (dst[i] < 0 || dst[i] >= c->npoin) return false;
+        }
+        return true;
+    };
+    std::vector<int64_t> s0, r0, b0;
+    if (!to0(send_i, ns, s0) || !to0(recv_idx, nr, r0) || !to0(recvback_idx, ns, b0))
+        return fail(c, JX_EINVAL, "halo list holds ids outside 1..npoin");
+    // owner-side adds keep list order per node: entries of one peer list are split into rounds
+    // (round k = k-th occurrence of a node in that list); each round is conflict free.
+    std::vector<int64_t> sel;
+    c->add_rounds.resize(c->recv_seg.size());
+    {
+        std::vector<int32_t> occ_count((size_t)c->npoin, 0);
+        for (size_t s = 0; s < c->recv_seg.size(); ++s) {
+            const PeerSeg &sg = c->recv_seg[s];
+            std::vector<int32_t> occ((size_t)sg.len);
+            int32_t maxocc = 0;
+            for (int64_t i = 0; i < sg.len; ++i) { occ[i] = occ_count[r0[sg.off + i]]++; maxocc = std::max(maxocc, occ[i]); }
+            for (int64_t i = 0; i < sg.len; ++i) occ_count[r0[sg.off + i]] = 0;
+            for (int32_t k = 0; k <= maxocc; ++k) {
+                AddRound rd{(int64_t)sel.size(), 0};
+                for (int64_t i = 0; i < sg.len; ++i)
+                    if (occ[i] == k) sel.push_back(sg.off + i);
+                rd.len = (int64_t)sel.size() - rd.off;
+                c->add_rounds[s].push_back(rd);
+            }
+        }
+    }
+    c->nsend = ns; c->nrecv = nr;
+    int rc;
+    if ((rc = dalloc(c, &c->d_send_i, (size_t)ns)) || (rc = dalloc(c, &c->d_recv_idx, (size_t)nr)) ||
+        (rc = dalloc(c, &c->d_recvback_idx, (size_t)ns)) || (rc = dalloc(c, &c->d_sendbuf, (size_t)ns * c->neqs)) ||
+        (rc = dalloc(c, &c->d_recvbuf, (size_t)nr * c->neqs)) || (rc = dalloc(c, &c->d_add_sel, sel.size())))
+        return rc;
+    CK(cudaMemcpy(c->d_send_i, s0.data(), (size_t)ns * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_recv_idx, r0.data(), (size_t)nr * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_recvback_idx, b0.data(), (size_t)ns * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_add_sel, sel.data(), sel.size() * 8, cudaMemcpyHostToDevice));
+    c->have_halo = true;
+    return JX_OK;
+}
+
+extern "C" int jx_set_state(jx_ctx *c, const double *u) {
+    if (!c || !u) return JX_EINVAL;
+    if (!c->have_mesh) return fail(c, JX_ESTATE, "jx_set_state before jx_upload_mesh");
+    cudaSetDevice(c->device);
+    CK(cudaMemcpyAsync(c->u, u, (size_t)c->npoin * c->neqs * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return JX_OK;
+}
+extern "C" int jx_get_state(jx_ctx *c, double *u) {
+    if (!c || !u) return JX_EINVAL;
+    if (!c->have_mesh) return fail(c, JX_ESTATE, "jx_get_state before jx_upload_mesh");
+    cudaSetDevice(c->device);
+    CK(cudaMemcpyAsync(u, c->u, (size_t)c->npoin * c->neqs * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return JX_OK;
+}
+extern "C" int jx_get_du(jx_ctx *c, double *du) {
+    if (!c || !du) return JX_EINVAL;
+    if (!c->have_mesh) return fail(c, JX_ESTATE, "jx_get_du before jx_upload_mesh");
+    cudaSetDevice(c->device);
+    CK(cudaMemcpyAsync(du, c->du, (size_t)c->npoin * c->neqs * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return JX_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the per-stage pipeline
+// ------------------------------------------------------------------------------------------
+namespace {
+
+// assemble_mpi! (mpi_communications.jl:260-338) on the device: pack -> owners add in ascending
+// sender rank, list order -> owners pack the sums -> send back -> non-owners overwrite.
+int assemble(jx_ctx *c, double *a) {
+    const int m = c->neqs;
+    const int64_t N = c->npoin;
+    cudaStream_t s = c->stream;
+    if (c->nsend > 0) {
+        k_pack<<<nblk(c->nsend * m, 256), 256, 0, s>>>(a, N, m, c->d_send_i, c->nsend, c->d_sendbuf);
+        c->launches++;
+    }
+    auto exchange = [&](bool back) -> int {
+        // forward: sendbuf segments -> owners' recvbuf segments; back: recvbuf segments -> sendbuf segments
+        const std::vector<PeerSeg> &out = back ? c->recv_seg : c->send_seg;
+        const std::vector<PeerSeg> &in = back ? c->send_seg : c->recv_seg;
+        double *obuf = back ? c->d_recvbuf : c->d_sendbuf;
+        double *ibuf = back ? c->d_sendbuf : c->d_recvbuf;
+        bool remote = false;
+        for (const PeerSeg &g : out) remote |= (g.peer != c->rank);
+        for (const PeerSeg &g : in) remote |= (g.peer != c->rank);
+        if (remote) {
+            NCK(nccl().GroupStart());
+            for (const PeerSeg &g : out)
+                if (g.peer != c->rank) NCK(nccl().Send(obuf + g.off * m, (size_t)(g.len * m), kNcclFloat64, g.peer, c->comm, s));
+            for (const PeerSeg &g : in)
+                if (g.peer != c->rank) NCK(nccl().Recv(ibuf + g.off * m, (size_t)(g.len * m), kNcclFloat64, g.peer, c->comm, s));
+            NCK(nccl().GroupEnd());
+        }
+        for (const PeerSeg &g : out)
+            if (g.peer == c->rank)
+                for (const PeerSeg &h : in)
+                    if (h.peer == c->rank)   // the reference's MPI self-send (periodic twins on one rank)
+                        CK(cudaMemcpyAsync(ibuf + h.off * m, obuf + g.off * m, (size_t)(g.len * m) * 8, cudaMemcpyDeviceToDevice, s));
+        return JX_OK;
+    };
+    int rc = exchange(false);
+    if (rc) return rc;
+    for (size_t sgi = 0; sgi < c->recv_seg.size(); ++sgi)          // ascending sender rank
+        for (const AddRound &rd : c->add_rounds[sgi]) {
+            if (rd.len == 0) continue;
+            k_add_sel<<<nblk(rd.len * m, 256), 256, 0, s>>>(a, N, m, c->d_recv_idx, c->d_add_sel + rd.off, rd.len, c->d_recvbuf);
+            c->launches++;
+        }
+    if (c->nrecv > 0) {
+        k_pack<<<nblk(c->nrecv * m, 256), 256, 0, s>>>(a, N, m, c->d_recv_idx, c->nrecv, c->d_recvbuf);
+        c->launches++;
+    }
+    rc = exchange(true);
+    if (rc) return rc;
+    if (c->nsend > 0) {
+        k_unpack<<<nblk(c->nsend * m, 256), 256, 0, s>>>(a, N, m, c->d_recvback_idx, c->nsend, c->d_sendbuf);
+        c->launches++;
+    }
+    return JX_OK;
+}
+
+struct StageUpdate {
+    int kind = 0;          // 0: du = Minv*RHS only; 1: 2N low-storage update of (u, tmp)
+    double A = 0, B = 0, dt = 0;
+    int first = 0;
+};
+
+// rhs!(du, u, params, t) on the device (rhs.jl:121-134, 498-711).  `u` is projected in place by
+// the Dirichlet kernel; the mass-scaled result lands in `du`; with upd.kind == 1 the low-storage
+// stage update is applied to (u, tmp) as well (fused into the DSS gather when no exchange follows).
+int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
+    const KernelSet *ks = c->ks;
+    cudaStream_t s = c->stream;
+    const int64_t N = c->npoin, E = c->nelem;
+    const int q = c->neqs;
+    if (c->nb > 0) {                                                     // rhs.jl:558
+        PhaseScope ps(c, PH_BC);
+        BcArgs b;
+        b.u = u; b.qe = c->qe; b.node = c->bc_node; b.ptr = c->bc_ptr; b.normal = c->bc_normal; b.npoin = N; b.nb = c->nb;
+        ks->launch_bc(b, s);
+        c->launches++;
+    }
+    const bool atomics = c->dss_mode == 1;
+    if (!atomics && (!c->rhs_el || (c->lvisc && !c->rhs_el_visc))) {
+        int rc;
+        if (!c->rhs_el && (rc = dalloc(c, &c->rhs_el, (size_t)E * c->np * q))) return rc;
+        if (c->lvisc && !c->rhs_el_visc && (rc = dalloc(c, &c->rhs_el_visc, (size_t)E * c->np * q))) return rc;
+    }
+    ElemArgs ea;
+    ea.u = u; ea.qe = c->qe; ea.rec = c->rec; ea.rhs_el = c->rhs_el; ea.rhs_el_visc = c->rhs_el_visc; ea.du = du;
+    ea.Minv = c->Minv; ea.coords = c->coords; ea.elist = nullptr; ea.nelem = E; ea.npoin = N;
+    ea.atomics = atomics ? 1 : 0; ea.lsource = c->lsource; ea.phys = c->phys;
+    for (int i = 0; i < 8; ++i) ea.visc[i] = c->visc[i];
+    for (int i = 0; i < 64; ++i) ea.dpsi[i] = c->dpsi[i];
+    // atomics mode folds M^-1 into the scatter unless an exchange of un-scaled sums follows
+    const bool fold_minv = atomics && !c->have_halo;
+    if (atomics) {
+        PhaseScope ps(c, PH_DSS);
+        CK(cudaMemsetAsync(du, 0, (size_t)N * q * 8, s));
+        if (!fold_minv) ea.Minv = nullptr;
+    }
+    if (E > 0) {
+        PhaseScope ps(c, PH_ELEM);
+        const int64_t ngroups = (E + ks->elems_per_block - 1) / ks->elems_per_block;
+        const int per_sm = std::max(1, ks->max_blocks_per_sm());
+        const int grid = (int)std::min<int64_t>(ngroups, (int64_t)c->num_sms * per_sm);
+        ks->launch_elem(ea, grid, s);                                    // rhs.jl:611, 659
+        c->launches++;
+    }
+    if (!atomics) {
+        PhaseScope ps(c, PH_DSS);
+        GatherArgs g;
+        g.rhs_el = c->rhs_el; g.rhs_el_visc = c->lvisc ? c->rhs_el_visc : nullptr; g.ptr = c->n2e_ptr; g.idx = c->n2e_idx;
+        g.Minv = c->Minv; g.out = du; g.u = u; g.tmp = c->tmp; g.npoin = N; g.np = c->np; g.neqs = q;
+        g.A = upd.A; g.B = upd.B; g.dt = upd.dt; g.first_stage = upd.first;
+        g.mode = c->have_halo ? 0 : (upd.kind == 1 ? 2 : 1);            // rhs.jl:624, 671-672, 698-699
+        ks->launch_gather(g, s);
+        c->launches++;
+        if (!c->have_halo) { CK(cudaGetLastError()); return JX_OK; }
+    }
+    if (c->have_halo) {                                                  // DSS_global_RHS!, rhs.jl:690
+        {
+            PhaseScope ps(c, PH_HALO);
+            int rc = assemble(c, du);
+            if (rc) return rc;
+        }
+        PhaseScope ps(c, PH_UPDATE);
+        k_scale_minv<<<nblk(N * q, 256), 256, 0, s>>>(du, c->Minv, N, q);   // rhs.jl:698-699
+        c->launches++;
+    }
+    if (upd.kind == 1) {
+        PhaseScope ps(c, PH_UPDATE);
+        k_lsrk_update<<<nblk(N * q, 256), 256, 0, s>>>(u, c->tmp, du, N * q, upd.A, upd.B, upd.dt, upd.first);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    return JX_OK;
+}
+
+int lincomb(jx_ctx *c, double *y, int form, int nterms, const double *const *x, const double *coef) {
+    LinArgs a;
+    a.y = y; a.nterms = nterms; a.n = c->npoin * c->neqs; a.form = form;
+    for (int i = 0; i < 5; ++i) { a.x[i] = i < nterms ? x[i] : nullptr; a.c[i] = i < nterms ? coef[i] : 0.0; }
+    if (a.n > 0) k_lincomb<<<nblk(a.n, 256), 256, 0, c->stream>>>(a);
+    c->launches++;
+    return JX_OK;
+}
+
+// Carpenter & Kennedy (1994) 2N-storage RK4(5) -- OrdinaryDiffEq CarpenterKennedy2N54
+const double CK_A[5] = {0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                        -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+const double CK_B[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
+                        1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
+                        2277821191437.0 / 14882151754819.0};
+
+int ensure_scratch(jx_ctx *c, int n) {
+    for (int i = 0; i < n; ++i)
+        if (!c->ss[i]) {
+            int rc = dalloc(c, &c->ss[i], (size_t)c->npoin * c->neqs);
+            if (rc) return rc;
+        }
+    return JX_OK;
+}
+
+}  // namespace
+
+extern "C" int jx_rhs(jx_ctx *c, double t, const double *u_host, double *du_host, double *u_back_host) {
+    (void)t;   // none of the registered hooks depends on time
+    if (!c) return JX_EINVAL;
+    if (!c->have_mesh) return fail(c, JX_ESTATE, "jx_rhs before jx_upload_mesh");
+    cudaSetDevice(c->device);
+    const size_t bytes = (size_t)c->npoin * c->neqs * 8;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (u_host) CK(cudaMemcpyAsync(c->u, u_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    StageUpdate upd;
+    int rc = rhs_core(c, c->u, c->du, upd);
+    if (rc) return rc;
+    if (du_host) CK(cudaMemcpyAsync(du_host, c->du, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (u_back_host) CK(cudaMemcpyAsync(u_back_host, c->u, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    if (u_host || du_host || u_back_host) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    }
+    return JX_OK;
+}
+
+extern "C" int jx_step(jx_ctx *c, int scheme, double t, double dt, int nsteps) {
+    (void)t;
+    if (!c) return JX_EINVAL;
+    if (!c->have_mesh) return fail(c, JX_ESTATE, "jx_step before jx_upload_mesh");
+    if (nsteps < 0) return fail(c, JX_EINVAL, "nsteps < 0");
+    cudaSetDevice(c->device);
+    const size_t bytes = (size_t)c->npoin * c->neqs * 8;
+    int rc;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (scheme == JX_SCHEME_CK2N54) {
+        for (int n = 0; n < nsteps; ++n)
+            for (int i = 0; i < 5; ++i) {
+                StageUpdate upd;
+                upd.kind = 1; upd.A = CK_A[i]; upd.B = CK_B[i]; upd.dt = dt; upd.first = (i == 0);
+                if ((rc = rhs_core(c, c->u, c->du, upd))) return rc;
+            }
+    } else if (scheme == JX_SCHEME_SSPRK33) {
+        // OrdinaryDiffEq SSPRK33 perform_step! (FSAL): k = f(uprev) is evaluated on the state itself
+        if ((rc = ensure_scratch(c, 1))) return rc;
+        double *up = c->ss[0], *u = c->u, *k = c->du;
+        StageUpdate none;
+        for (int n = 0; n < nsteps; ++n) {
+            if ((rc = rhs_core(c, u, k, none))) return rc;
+            CK(cudaMemcpyAsync(up, u, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            { const double *x[2] = {u, k}; double cf[2] = {1.0, dt}; lincomb(c, u, 0, 2, x, cf); }
+            if ((rc = rhs_core(c, u, k, none))) return rc;
+            { const double *x[3] = {up, u, k}; double cf[3] = {3.0, 1.0, dt}; lincomb(c, u, 1, 3, x, cf); }
+            if ((rc = rhs_core(c, u, k, none))) return rc;
+            { const double *x[3] = {up, u, k}; double cf[3] = {1.0, 2.0, 2 * dt}; lincomb(c, u, 2, 3, x, cf); }
+        }
+        if (nsteps > 0 && (rc = rhs_core(c, u, k, none))) return rc;   // trailing FSAL evaluation projects the final state
+    } else if (scheme == JX_SCHEME_SSPRK54) {
+        // Spiteri & Ruuth (2002) SSPRK(5,4) in OrdinaryDiffEq's update form
+        if ((rc = ensure_scratch(c, 5))) return rc;
+        const double b10 = 0.391752226571890, a20 = 0.444370493651235, a21 = 0.555629506348765, b21 = 0.368410593050371,
+                     a30 = 0.620101851488403, a32 = 0.379898148511597, b32 = 0.251891774271694, a40 = 0.178079954393132,
+                     a43 = 0.821920045606868, b43 = 0.544974750228521, a52 = 0.517231671970585, a53 = 0.096059710526147,
+                     b53 = 0.063692468666290, a54 = 0.386708617503269, b54 = 0.226007483236906;
+        double *up = c->ss[0], *u2 = c->ss[1], *u3 = c->ss[2], *u4 = c->ss[3], *k3 = c->ss[4], *u = c->u, *k = c->du;
+        StageUpdate none;
+        for (int n = 0; n < nsteps; ++n) {
+            if ((rc = rhs_core(c, u, k, none))) return rc;
+            CK(cudaMemcpyAsync(up, u, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            { const double *x[2] = {up, k}; double cf[2] = {1.0, b10 * dt}; lincomb(c, u2, 0, 2, x, cf); }
+            if ((rc = rhs_core(c, u2, k, none))) return rc;
+            { const double *x[3] = {up, u2, k}; double cf[3] = {a20, a21, b21 * dt}; lincomb(c, u2, 0, 3, x, cf); }
+            if ((rc = rhs_core(c, u2, k, none))) return rc;
+            { const double *x[3] = {up, u2, k}; double cf[3] = {a30, a32, b32 * dt}; lincomb(c, u3, 0, 3, x, cf); }
+            if ((rc = rhs_core(c, u3, k3, none))) return rc;
+            { const double *x[3] = {up, u3, k3}; double cf[3] = {a40, a43, b43 * dt}; lincomb(c, u4, 0, 3, x, cf); }
+            if ((rc = rhs_core(c, u4, k, none))) return rc;
+            { const double *x[5] = {u2, u3, k3, u4, k}; double cf[5] = {a52, a53, b53 * dt, a54, b54 * dt}; lincomb(c, u, 0, 5, x, cf); }
+        }
+        if (nsteps > 0 && (rc = rhs_core(c, u, k, none))) return rc;
+    } else {
+        return fail(c, JX_EINVAL, "unknown scheme %d", scheme);
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    return JX_OK;
+}
+
+extern "C" int jx_last_elapsed_ms(jx_ctx *c, float *ms) {
+    if (!c || !ms) return JX_EINVAL;
+    *ms = c->last_ms;
+    return JX_OK;
+}
+extern "C" int64_t jx_launch_count(jx_ctx *c) { return c ? c->launches : 0; }
+extern "C" int jx_sync(jx_ctx *c) {
+    if (!c) return JX_EINVAL;
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream));
+    return JX_OK;
+}
+
+extern "C" int jx_bench_rhs(jx_ctx *c, int n, int fused_stage, float *total_ms, float *phase_ms) {
+    if (!c || n <= 0) return JX_EINVAL;
+    if (!c->have_mesh) return fail(c, JX_ESTATE, "jx_bench_rhs before jx_upload_mesh");
+    cudaSetDevice(c->device);
+    for (auto e : c->ph_ev) cudaEventDestroy(e);
+    c->ph_ev.clear(); c->ph_tag.clear();
+    c->phase_timing = phase_ms != nullptr;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    int rc = JX_OK;
+    for (int i = 0; i < n && rc == JX_OK; ++i) {
+        StageUpdate upd;
+        if (fused_stage) {   // a dt = 0 CK2N54 stage: full stage traffic, state unchanged
+            upd.kind = 1; upd.A = CK_A[1]; upd.B = CK_B[1]; upd.dt = 0.0; upd.first = 0;
+        }
+        rc = rhs_core(c, c->u, c->du, upd);
+    }
+    c->phase_timing = false;
+    if (rc) return rc;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    if (total_ms) *total_ms = c->last_ms;
+    if (phase_ms) {
+        for (int i = 0; i < PH_COUNT; ++i) phase_ms[i] = 0.f;
+        for (size_t k = 0; k < c->ph_tag.size(); ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->ph_ev[2 * k], c->ph_ev[2 * k + 1]);
+            phase_ms[c->ph_tag[k]] += ms;
+        }
+    }
+    return JX_OK;
+}

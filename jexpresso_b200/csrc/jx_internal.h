@@ -1,0 +1,31 @@
+// jx_internal.h -- host-side glue between the C ABI (jexrhs.cu) and the kernel instantiation
+// units (jx_inst_*.cu).  Not part of the public interface.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "jx_kernels.cuh"
+
+namespace jx {
+
+// One (nsd, ngl, equation set, PERT/TOTAL, pow mode, viscous on/off) combination = one set of
+// compiled kernels.  The launchers are plain function pointers so jexrhs.cu never sees the templates.
+struct KernelSet {
+    int nsd, ngl, eq_id, lpert, jxpow, lvisc, variant;
+    int neq;
+    int elems_per_block;
+    int nthreads;
+    size_t smem_bytes;
+    cudaError_t (*prepare)();                                   // cudaFuncSetAttribute(s)
+    int (*max_blocks_per_sm)();                                 // occupancy of the element kernel
+    void (*launch_elem)(const ElemArgs &, int grid, cudaStream_t);
+    void (*launch_bc)(const BcArgs &, cudaStream_t);
+    void (*launch_gather)(const GatherArgs &, cudaStream_t);
+};
+
+// each instantiation unit exports one lookup; returns nullptr if it does not hold the combination
+const KernelSet *lookup_euler_theta_3d(int ngl, int lpert, int jxpow, int lvisc, int variant);
+const KernelSet *lookup_euler_theta_2d(int ngl, int lpert, int jxpow, int lvisc, int variant);
+const KernelSet *lookup_other(int nsd, int ngl, int eq_id, int lvisc, int variant);
+
+}  // namespace jx

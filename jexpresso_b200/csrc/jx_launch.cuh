@@ -1,0 +1,60 @@
+// jx_launch.cuh -- turns one template combination into a KernelSet of plain function pointers.
+#pragma once
+#include "jx_internal.h"
+
+namespace jx {
+
+template <int NSD, int NGL>
+constexpr int default_epb() {
+    constexpr int np = Geo<NSD, NGL>::NP;
+    return np >= 256 ? 1 : (256 / np);
+}
+
+template <int NSD, int NGL, class EQ, bool VISC>
+struct NodeKernel {
+    static constexpr int EPB = default_epb<NSD, NGL>();
+    using C = ElemNodeCfg<NSD, NGL, EQ, VISC, EPB>;
+    static cudaError_t prepare() {
+        return cudaFuncSetAttribute(k_elem_node<NSD, NGL, EQ, VISC, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)C::SMEM_BYTES);
+    }
+    static int max_blocks() {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_node<NSD, NGL, EQ, VISC, EPB>, C::NT, C::SMEM_BYTES);
+        return nb;
+    }
+    static void launch(const ElemArgs &a, int grid, cudaStream_t s) {
+        k_elem_node<NSD, NGL, EQ, VISC, EPB><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+    }
+};
+
+template <class EQ>
+void launch_bc_t(const BcArgs &a, cudaStream_t s) {
+    if (a.nb <= 0) return;
+    k_bc_dirichlet<EQ><<<(a.nb + 127) / 128, 128, 0, s>>>(a);
+}
+
+template <int NEQ>
+void launch_gather_t(const GatherArgs &a, cudaStream_t s) {
+    if (a.npoin <= 0) return;
+    k_gather<NEQ><<<(unsigned)((a.npoin + 255) / 256), 256, 0, s>>>(a);
+}
+
+template <int NSD, int NGL, class EQ, bool VISC>
+KernelSet make_node_set(int eq_id, int lpert, int jxpow) {
+    using K = NodeKernel<NSD, NGL, EQ, VISC>;
+    KernelSet ks;
+    ks.nsd = NSD; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = VISC; ks.variant = 0;
+    ks.neq = EQ::NEQ;
+    ks.elems_per_block = K::EPB;
+    ks.nthreads = K::C::NT;
+    ks.smem_bytes = K::C::SMEM_BYTES;
+    ks.prepare = &K::prepare;
+    ks.max_blocks_per_sm = &K::max_blocks;
+    ks.launch_elem = &K::launch;
+    ks.launch_bc = &launch_bc_t<EQ>;
+    ks.launch_gather = &launch_gather_t<EQ::NEQ>;
+    return ks;
+}
+
+}  // namespace jx

@@ -1,0 +1,150 @@
+"""GPU parity proper: libjexrhs (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Bars (BASELINE.json north_star): <= 1e-12 relative per node and <= 1e-10 relative L2
+after one RHS; with the shared deterministic pow (JX_OPT_POW_MODE=1) and the deterministic DSS
+gather the element arithmetic is the same sequence of IEEE operations as the oracle's, so those
+cases are additionally required to be BIT-EXACT."""
+import numpy as np
+import pytest
+
+from helpers import MU2, MU3, PHYS, box2d, box3d, euler_case, rel_err_per_node
+from jexpresso_b200 import rhs as jrhs
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(lpert, lvisc, nsd):
+    return {"SOL_VARS_TYPE": "PERT" if lpert else "TOTAL", "lsource": True, "lvisc": lvisc,
+            "mu": MU3 if nsd == 3 else MU2, "dt": 0.4, "ode_solver": "CarpenterKennedy2N54"}
+
+
+def _oracle_rhs(sems, qes, us, lpert, lvisc, pow_mode, caches=None):
+    nsd = sems[0].mesh.nsd
+    probs = [ref.RefProblem(s, qe, eq_id=0, lpert=lpert, lsource=True, lvisc=lvisc, visc_coeff=MU3 if nsd == 3 else MU2,
+                            phys=PHYS, pow_mode=pow_mode) for s, qe in zip(sems, qes)]
+    run = ref.RefRun(probs, caches)
+    u2 = [u.copy() for u in us]
+    dus = [np.zeros_like(u) for u in us]
+    run.rhs(dus, u2, 0.0)
+    return dus, u2, run
+
+
+@pytest.mark.parametrize("nop", [2, 4, 5, 7])
+@pytest.mark.parametrize("lpert", [False, True])
+@pytest.mark.parametrize("lvisc", [False, True])
+def test_one_rhs_3d_bit_exact(nop, lpert, lvisc):
+    nel = (3, 2, 2) if nop >= 5 else (4, 3, 3)
+    spec = box3d(nel, nop, warp=0.05)
+    sems, qns, qes, us = euler_case(spec, 1, lpert=lpert)
+    dus, ub, _ = _oracle_rhs(sems, qes, us, lpert, lvisc, pow_mode=1)
+    p = jrhs.params_setup(sems[0], qes[0], _inputs(lpert, lvisc, 3), pow_mode=1, dss_mode=0)
+    try:
+        u = us[0].copy()
+        du = np.empty_like(u)
+        jrhs.rhs_bang(du, u, p, 0.0)
+    finally:
+        p.close()
+    assert np.array_equal(u, ub[0]), "boundary-projected state differs from the oracle"
+    assert np.array_equal(du, dus[0]), rel_err_per_node(du, dus[0])
+
+
+@pytest.mark.parametrize("nop", [2, 4, 5, 7])
+@pytest.mark.parametrize("lpert", [False, True])
+def test_one_rhs_2d_bit_exact(nop, lpert):
+    spec = box2d((6, 5), nop, warp=0.05)
+    sems, qns, qes, us = euler_case(spec, 1, lpert=lpert)
+    dus, ub, _ = _oracle_rhs(sems, qes, us, lpert, True, pow_mode=1)
+    p = jrhs.params_setup(sems[0], qes[0], _inputs(lpert, True, 2), pow_mode=1, dss_mode=0)
+    try:
+        u = us[0].copy()
+        du = np.empty_like(u)
+        jrhs.rhs_bang(du, u, p, 0.0)
+    finally:
+        p.close()
+    assert np.array_equal(u, ub[0])
+    assert np.array_equal(du, dus[0]), rel_err_per_node(du, dus[0])
+
+
+@pytest.mark.parametrize("dss_mode,pow_mode", [(1, 1), (0, 0), (1, 0)])
+def test_one_rhs_3d_tolerance_modes(dss_mode, pow_mode):
+    """Atomics DSS (unordered sums) and CUDA pow (different <2 ulp pow): inside the north-star
+    tolerance against the oracle evaluated with libm pow."""
+    spec = box3d((5, 4, 4), 4, warp=0.05)
+    for lpert in (False, True):
+        sems, qns, qes, us = euler_case(spec, 1, lpert=lpert)
+        dus, ub, _ = _oracle_rhs(sems, qes, us, lpert, True, pow_mode=0)
+        p = jrhs.params_setup(sems[0], qes[0], _inputs(lpert, True, 3), pow_mode=pow_mode, dss_mode=dss_mode)
+        try:
+            u = us[0].copy()
+            du = np.empty_like(u)
+            jrhs.rhs_bang(du, u, p, 0.0)
+        finally:
+            p.close()
+        N = sems[0].mesh.npoin
+        for e in range(5):
+            pn, l2 = rel_err_per_node(du[e * N:(e + 1) * N], dus[0][e * N:(e + 1) * N])
+            assert pn <= 1e-12 and l2 <= 1e-10, (lpert, e, pn, l2)
+
+
+def test_config2_one_rhs_and_100_steps():
+    """BASELINE config 2: CompEuler 3D rising thermal bubble, nop=4, 10x10x10 elements, AV."""
+    spec = box3d((10, 10, 10), 4)
+    lpert = False
+    sems, qns, qes, us = euler_case(spec, 1, lpert=lpert, vel_amp=0.0 + 1.0)
+    dus, ub, run = _oracle_rhs(sems, qes, us, lpert, True, pow_mode=1)
+    inputs = _inputs(lpert, True, 3)
+    p = jrhs.params_setup(sems[0], qes[0], inputs, pow_mode=1, dss_mode=0)
+    try:
+        u = us[0].copy()
+        du = np.empty_like(u)
+        jrhs.rhs_bang(du, u, p, 0.0)
+        assert np.array_equal(du, dus[0])
+        # 100 CK2N54 steps, all stages on the device, against the oracle's time loop
+        ug = us[0].copy()
+        jrhs.time_loop_bang(inputs, p, ug, 100)
+    finally:
+        p.close()
+    uo = [us[0].copy()]
+    ref.time_loop(run, uo, 0.0, inputs["dt"], 100, scheme="CK2N54")
+    N = sems[0].mesh.npoin
+    for e in range(5):
+        pn, l2 = rel_err_per_node(ug[e * N:(e + 1) * N], uo[0][e * N:(e + 1) * N])
+        assert pn <= 1e-12 and l2 <= 1e-10, (e, pn, l2)
+    assert np.array_equal(ug, uo[0]), "deterministic modes should reproduce the oracle bit for bit"
+
+
+@pytest.mark.parametrize("scheme", ["SSPRK33", "SSPRK54"])
+def test_ssprk_schemes_2d(scheme):
+    spec = box2d((8, 8), 4)
+    sems, qns, qes, us = euler_case(spec, 1, lpert=True, seed=None)
+    probs = [ref.RefProblem(sems[0], qes[0], eq_id=0, lpert=True, lsource=True, lvisc=True, visc_coeff=MU2, phys=PHYS, pow_mode=1)]
+    run = ref.RefRun(probs)
+    uo = [us[0].copy()]
+    ref.time_loop(run, uo, 0.0, 0.3, 20, scheme=scheme)
+    inputs = _inputs(True, True, 2)
+    inputs.update(dt=0.3, ode_solver=scheme)
+    p = jrhs.params_setup(sems[0], qes[0], inputs, pow_mode=1)
+    try:
+        ug = us[0].copy()
+        jrhs.time_loop_bang(inputs, p, ug, 20)
+    finally:
+        p.close()
+    assert np.array_equal(ug, uo[0]), rel_err_per_node(ug, uo[0])
+
+
+def test_periodic_self_exchange_3d():
+    """Periodic x,y box on one rank: the twins are summed through the assembler's self lists
+    (the reference's MPI self-send, mpi_communications.jl:99-112)."""
+    spec = box3d((4, 4, 3), 4, periodic=(True, True, False))
+    sems, qns, qes, us = euler_case(spec, 1, lpert=False)
+    assert not sems[0].asm.is_trivial()
+    caches = ref.setup_assembler([sems[0].mesh.ip2gip], [sems[0].mesh.gip2owner])
+    dus, ub, _ = _oracle_rhs(sems, qes, us, False, True, pow_mode=1, caches=caches)
+    p = jrhs.params_setup(sems[0], qes[0], _inputs(False, True, 3), pow_mode=1)
+    try:
+        u = us[0].copy()
+        du = np.empty_like(u)
+        jrhs.rhs_bang(du, u, p, 0.0)
+    finally:
+        p.close()
+    assert np.array_equal(du, dus[0]), rel_err_per_node(du, dus[0])

@@ -1,0 +1,53 @@
+"""Pins the CPU oracle (oracle/jexref.c + oracle/ref.py) against the reference's OWN golden end
+state for this path: test/CI-ref/CompEuler/theta (2D theta-form Euler, PERT, AV mu=125, 2000
+CarpenterKennedy2N54 steps of dt=0.5 on the 10x10 nop=4 box; reference tolerance atol=1e-5,
+test/ci_cases.jl:57,73).  The HDF5 files carry no coordinates and follow Gridap's node numbering,
+so the comparison is order free: the sorted nodal values of every variable must agree."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import MU2, PHYS, box2d, euler_case
+from oracle import ref
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "CompEuler_theta.npz")
+
+
+@pytest.fixture(scope="module")
+def theta_end_state():
+    spec = box2d((10, 10), 4)
+    sems, qns, qes, us = euler_case(spec, 1, lpert=True, seed=None)
+    prob = ref.RefProblem(sems[0], qes[0], eq_id=0, lpert=True, lsource=True, lvisc=True, visc_coeff=MU2, phys=PHYS, pow_mode=0)
+    run = ref.RefRun([prob])
+    t = ref.time_loop(run, us, 0.0, 0.5, 2000, scheme="CK2N54")
+    return sems[0], qes[0], us[0], t
+
+
+def test_theta_golden_end_state(theta_end_state):
+    sem, qe, u, t = theta_end_state
+    g = np.load(GOLD)
+    assert abs(t - 1000.0) < 1e-9 and abs(float(g["t_time"][0]) - 1000.0) < 1e-6
+    N = sem.mesh.npoin
+    assert N == g["q1"].shape[0] == 1681
+    worst = 0.0
+    for i in range(4):
+        mine = np.sort(u[i * N:(i + 1) * N])
+        gold = np.sort(g[f"q{i + 1}"])
+        worst = max(worst, float(np.max(np.abs(mine - gold))))
+        assert np.allclose(mine, gold, rtol=0.0, atol=1e-5), f"variable {i + 1} outside the reference's CI tolerance"
+        assert np.allclose(np.sort(qe[:, i]), np.sort(g[f"qe{i + 1}"]), rtol=0.0, atol=1e-9)
+    # far inside the reference's own tolerance: the restatement tracks the real Julia run closely
+    assert worst < 1e-8, worst
+
+
+def test_theta_golden_moments(theta_end_state):
+    """Order-free moments (sum, sum of squares, extrema) of the end state, per variable."""
+    sem, qe, u, t = theta_end_state
+    g = np.load(GOLD)
+    N = sem.mesh.npoin
+    for i in range(4):
+        a, b = u[i * N:(i + 1) * N], g[f"q{i + 1}"]
+        for f in (np.sum, np.min, np.max, lambda v: np.sum(v * v)):
+            fa, fb = float(f(a)), float(f(b))
+            assert abs(fa - fb) <= 1e-5 * max(1.0, abs(fb)) * 10
