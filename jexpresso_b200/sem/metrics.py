@@ -38,14 +38,19 @@ def build_metric_terms(mesh, basis):
         shp = X.shape
 
         def deriv(C, axis):
-            out = np.zeros(shp)
+            # out[.., l, ..] = sum_i dpsi[i, l] * C[.., i, ..], ascending i, multiply then add
+            # (slices are views; no gather copies)
+            out = np.empty(shp)
+            tmp = np.empty(shp[:axis] + shp[axis + 1:])
             for l in range(n):
-                acc = np.zeros(shp[:axis] + shp[axis + 1:])
-                for i in range(n):          # ascending i, mul then add
-                    acc = acc + dpsi[i, l] * np.take(C, i, axis=axis)
                 idx = [slice(None)] * 4
                 idx[axis] = l
-                out[tuple(idx)] = acc
+                acc = out[tuple(idx)]
+                acc[...] = 0.0
+                for i in range(n):
+                    idx[axis] = i
+                    np.multiply(C[tuple(idx)], dpsi[i, l], out=tmp)
+                    np.add(acc, tmp, out=acc)
             return out
 
         dxdxi, dxdeta, dxdzeta = deriv(X, 1), deriv(X, 2), deriv(X, 3)
@@ -73,14 +78,17 @@ def build_metric_terms(mesh, basis):
     shp = X.shape
 
     def deriv2(C, axis):
-        out = np.zeros(shp)
+        out = np.empty(shp)
+        tmp = np.empty(shp[:axis] + shp[axis + 1:])
         for l in range(n):
-            acc = np.zeros(shp[:axis] + shp[axis + 1:])
-            for i in range(n):
-                acc = acc + dpsi[i, l] * np.take(C, i, axis=axis)
             idx = [slice(None)] * 3
             idx[axis] = l
-            out[tuple(idx)] = acc
+            acc = out[tuple(idx)]
+            acc[...] = 0.0
+            for i in range(n):
+                idx[axis] = i
+                np.multiply(C[tuple(idx)], dpsi[i, l], out=tmp)
+                np.add(acc, tmp, out=acc)
         return out
 
     dxdxi, dxdeta = deriv2(X, 1), deriv2(X, 2)

@@ -205,7 +205,7 @@ class _CyclingReverseDict:
         return v[c % len(v)]
 
 
-def setup_assembler_all(ip2gip_list, owner_list):
+def setup_assembler_all(ip2gip_list, owner_list, only_rank=None):
     """Build the AssemblerCache index lists of every rank (mpi_communications.jl:75-234).
 
     The Alltoall / Isend / Irecv of the reference move ``send_idx`` (global ids) to the
@@ -231,7 +231,7 @@ def setup_assembler_all(ip2gip_list, owner_list):
                     si[rank].append(int(i))
         g2l.append(crd); send_idx.append(sidx); send_i.append(si)
     out = []
-    for rank in range(R):
+    for rank in (range(R) if only_rank is None else [only_rank]):
         crd = g2l[rank]
         recv_idx = [[crd.first(g) for g in send_idx[src][rank]] for src in range(R)]
         recvback = []
