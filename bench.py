@@ -20,7 +20,6 @@ import json
 import os
 import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -56,45 +55,56 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason samples taken DURING the timed region by an in-process NVML thread
+    (5 ms period; `nvidia-smi -lms` is too coarse for a 100 ms region)."""
 
     def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.sm, self.reasons, self.smax, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self._th = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+            return
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+
+    def _run(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, b in bits.items():
+                    if r & b:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": [], "samples": 0}
+        if self._th is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
-        os.unlink(self.f.name)
-        sm, reasons = [], set()
-        for r in rows:
-            if len(r) < 7:
-                continue
-            try:
-                sm.append(float(r[0]))
-                out["sm_max_mhz"] = float(r[1])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out["sm_mhz"] = float(np.median(sm))
-        out["reasons"] = sorted(reasons)
-        out["samples"] = len(sm)
+        self._stop.set()
+        self._th.join(timeout=2)
+        if self.sm:
+            out["sm_mhz"] = float(np.median(self.sm))
+            out["sm_min_mhz"] = float(np.min(self.sm))
+            out["power_w_max"] = float(np.max(self.power)) if self.power else None
+        out["reasons"] = sorted(self.reasons)
+        out["samples"] = len(self.sm)
         return out
 
 
@@ -314,7 +324,7 @@ def main():
                    "l2": "inputs (3.9 GB metric records + 1 GB state per GPU) >> 126 MB L2; no flush needed",
                    "dss_mode": a.dss_mode, "pow_mode": a.pow_mode, "elem_kernel": a.elem_kernel, "setup_s": round(setup_s, 1),
                    "phase_ms_per_step": {k: round(v / a.steps, 4) for k, v in
-                                         zip(("bc", "elem", "dss", "halo", "update"), phases[:5])},
+                                         zip(("bc", "elem", "dss", "halo", "update", "aux"), phases[:6])},
                    "fused_stage_ms_per_step": ms_f / a.steps,
                    "fused_stage_gdofs": total_dofs / (ms_f / a.steps * 1e-3) / 1e9},
         "roofline": {"bound": "hbm", "kernel": "k_elem (fused flux + divergence, per element)", "achieved": achieved,

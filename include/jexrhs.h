@@ -124,6 +124,11 @@ int jx_sync(jx_ctx *);
  * zero-fill in atomics mode), [3] interface exchange, [4] M^-1 / stage update passes. */
 int jx_bench_rhs(jx_ctx *, int n, int fused_stage, float *total_ms, float *phase_ms);
 
+/* device self tests (diagnostics for the parity suite, no reference counterpart).  which = 0: the shared-
+ * reciprocal division used by the two-stage flux functors against the compiler's correctly rounded `/` on n
+ * pseudo-random operand pairs; *failures receives the number of bitwise mismatches. */
+int jx_selftest(jx_ctx *, int which, int64_t n, int64_t *failures);
+
 #ifdef __cplusplus
 }
 #endif

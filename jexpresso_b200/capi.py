@@ -65,6 +65,7 @@ def lib():
     L.jx_launch_count.restype = i64
     L.jx_sync.argtypes = [vp]
     L.jx_bench_rhs.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+    L.jx_selftest.argtypes = [vp, i32, i64, ctypes.POINTER(i64)]
     _lib = L
     return L
 
@@ -194,6 +195,11 @@ class Context:
 
     def launch_count(self):
         return int(lib().jx_launch_count(self._h))
+
+    def selftest(self, which, n):
+        bad = ctypes.c_int64()
+        self._ck(lib().jx_selftest(self._h, int(which), int(n), ctypes.byref(bad)))
+        return bad.value
 
     def bench_rhs(self, n, fused_stage=False, phases=True):
         tot = ctypes.c_float()

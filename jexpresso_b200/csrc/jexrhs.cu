@@ -69,7 +69,7 @@ NcclApi &nccl() {
 // ------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------
-enum { PH_BC = 0, PH_ELEM = 1, PH_DSS = 2, PH_HALO = 3, PH_UPDATE = 4, PH_COUNT = 8 };
+enum { PH_BC = 0, PH_ELEM = 1, PH_DSS = 2, PH_HALO = 3, PH_UPDATE = 4, PH_AUX = 5, PH_COUNT = 8 };
 
 struct PeerSeg {
     int peer;
@@ -95,6 +95,7 @@ struct jx_ctx {
     Phys phys;
     const KernelSet *ks = nullptr;
     int np = 0, nmet = 0, rec_bytes = 0;
+    int rec_layout = -1;             // layout the resident element records were built with (-1: none)
 
     // options
     int dss_mode = 0, pow_mode = 0, elem_variant = 0;
@@ -102,6 +103,7 @@ struct jx_ctx {
     // device arrays
     double *u = nullptr, *du = nullptr, *tmp = nullptr, *qe = nullptr, *Minv = nullptr, *coords = nullptr;
     double *rhs_el = nullptr, *rhs_el_visc = nullptr;
+    double *aux = nullptr;           // per-node flux ingredient (k_node_aux), kernels with launch_aux only
     char *rec = nullptr;
     int64_t *n2e_ptr = nullptr;
     uint32_t *n2e_idx = nullptr;
@@ -193,9 +195,10 @@ struct PhaseScope {
 
 void free_mesh(jx_ctx *c) {
     dfree(c->u); dfree(c->du); dfree(c->tmp); dfree(c->qe); dfree(c->Minv); dfree(c->coords);
-    dfree(c->rhs_el); dfree(c->rhs_el_visc); dfree(c->rec); dfree(c->n2e_ptr); dfree(c->n2e_idx);
+    dfree(c->rhs_el); dfree(c->rhs_el_visc); dfree(c->aux); dfree(c->rec); dfree(c->n2e_ptr); dfree(c->n2e_idx);
     for (auto &p : c->ss) dfree(p);
     c->have_mesh = false;
+    c->rec_layout = -1;
 }
 void free_bcs(jx_ctx *c) {
     dfree(c->bc_node); dfree(c->bc_ptr); dfree(c->bc_normal);
@@ -221,6 +224,9 @@ int select_kernels(jx_ctx *c) {
         return fail(c, JX_EINVAL, "no kernel for nsd=%d ngl=%d eq=%d lpert=%d pow=%d lvisc=%d variant=%d", c->nsd, c->ngl,
                     c->eq_id, c->lpert, c->pow_mode, c->lvisc, c->elem_variant);
     if (ks->neq != c->neqs) return fail(c, JX_EINVAL, "equation set %d has %d equations, got neqs=%d", c->eq_id, ks->neq, c->neqs);
+    if (c->have_mesh && ks->rec_layout != c->rec_layout)
+        return fail(c, JX_ESTATE, "kernel variant %d reads element-record layout %d, the resident records have layout %d: "
+                    "set JX_OPT_ELEM_KERNEL before jx_upload_mesh", c->elem_variant, ks->rec_layout, c->rec_layout);
     CK(ks->prepare());
     c->ks = ks;
     return JX_OK;
@@ -288,6 +294,7 @@ extern "C" int jx_last_error(jx_ctx *c, char *buf, int len) {
 
 extern "C" int jx_set_option(jx_ctx *c, int key, int64_t value) {
     if (!c) return JX_EINVAL;
+    const int old_dss = c->dss_mode, old_pow = c->pow_mode, old_var = c->elem_variant;
     switch (key) {
         case JX_OPT_DSS_MODE:
             if (value != 0 && value != 1) return fail(c, JX_EINVAL, "dss mode must be 0 or 1");
@@ -300,7 +307,11 @@ extern "C" int jx_set_option(jx_ctx *c, int key, int64_t value) {
         case JX_OPT_ELEM_KERNEL: c->elem_variant = (int)value; break;
         default: return fail(c, JX_EINVAL, "unknown option %d", key);
     }
-    if (c->have_problem) return select_kernels(c);
+    if (c->have_problem) {
+        const int rc = select_kernels(c);
+        if (rc) { c->dss_mode = old_dss; c->pow_mode = old_pow; c->elem_variant = old_var; }   // refused: keep the working set
+        return rc;
+    }
     return JX_OK;
 }
 
@@ -376,6 +387,7 @@ extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *c
     RetileArgs ra;
     ra.omega = d_omega; ra.connijk = d_conn; ra.rec = c->rec; ra.nelem = E; ra.nsd = c->nsd; ra.ngl = c->ngl; ra.np = np;
     ra.nmet = c->nmet; ra.npp = (np + 3) / 4 * 4; ra.rec_bytes = c->rec_bytes; ra.src = nullptr;
+    ra.layout = c->ks->rec_layout;
     if (total > 0) {
         CKC(cudaMemsetAsync(c->rec, 0, (size_t)E * c->rec_bytes, c->stream));
         ra.slot = -1;
@@ -422,6 +434,7 @@ extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *c
     cleanup();
 #undef CKC
     c->have_mesh = true;
+    c->rec_layout = c->ks->rec_layout;
     return JX_OK;
 }
 
@@ -657,10 +670,19 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     for (int i = 0; i < 64; ++i) ea.dpsi[i] = c->dpsi[i];
     // atomics mode folds M^-1 into the scatter unless an exchange of un-scaled sums follows
     const bool fold_minv = atomics && !c->have_halo;
-    if (atomics) {
+    if (atomics && !fold_minv) ea.Minv = nullptr;
+    ea.aux = nullptr;
+    if (ks->launch_aux) {                                                // per-node flux ingredient (+ zero-fill of du)
+        PhaseScope ps(c, PH_AUX);
+        if (!c->aux) { int rc = dalloc(c, &c->aux, (size_t)N); if (rc) return rc; }
+        AuxArgs aa;
+        aa.u = u; aa.qe = c->qe; aa.aux = c->aux; aa.zero = atomics ? du : nullptr; aa.npoin = N; aa.phys = c->phys;
+        ks->launch_aux(aa, (int)std::min<int64_t>((N + 255) / 256, (int64_t)c->num_sms * 8), s);
+        c->launches++;
+        ea.aux = c->aux;
+    } else if (atomics) {
         PhaseScope ps(c, PH_DSS);
         CK(cudaMemsetAsync(du, 0, (size_t)N * q * 8, s));
-        if (!fold_minv) ea.Minv = nullptr;
     }
     if (E > 0) {
         PhaseScope ps(c, PH_ELEM);
@@ -821,6 +843,23 @@ extern "C" int jx_sync(jx_ctx *c) {
     if (!c) return JX_EINVAL;
     cudaSetDevice(c->device);
     CK(cudaStreamSynchronize(c->stream));
+    return JX_OK;
+}
+
+extern "C" int jx_selftest(jx_ctx *c, int which, int64_t n, int64_t *failures) {
+    if (!c || !failures || n < 0) return JX_EINVAL;
+    if (which != 0) return fail(c, JX_EINVAL, "unknown self test %d", which);
+    cudaSetDevice(c->device);
+    unsigned long long *d_bad = nullptr, h_bad = 0;
+    CK(cudaMalloc((void **)&d_bad, 8));
+    CK(cudaMemsetAsync(d_bad, 0, 8, c->stream));
+    if (n > 0) k_selftest_div<<<c->num_sms * 8, 256, 0, c->stream>>>(n, 0x1234abcdull, d_bad);
+    c->launches++;
+    cudaError_t e = cudaMemcpyAsync(&h_bad, d_bad, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_bad);
+    if (e != cudaSuccess) return fail(c, JX_ECUDA, "jx_selftest: %s", cudaGetErrorString(e));
+    *failures = (int64_t)h_bad;
     return JX_OK;
 }
 

@@ -9,8 +9,20 @@ namespace jx {
     JX_SET(NGL, false, true, true), JX_SET(NGL, true, false, false), JX_SET(NGL, true, false, true), \
     JX_SET(NGL, true, true, false), JX_SET(NGL, true, true, true)
 
+#define JX_PSET(NGL, PERT, POW, EXACT) make_pencil_set<NGL, EulerTheta<3, PERT, POW>, EXACT>(JX_EQ_EULER_THETA, PERT, POW)
+#define JX_PROW(NGL) \
+    JX_PSET(NGL, false, false, true), JX_PSET(NGL, false, true, true), JX_PSET(NGL, true, false, true), \
+    JX_PSET(NGL, true, true, true), JX_PSET(NGL, false, false, false), JX_PSET(NGL, false, true, false), \
+    JX_PSET(NGL, true, false, false), JX_PSET(NGL, true, true, false)
+
+#define JX_WSET(NGL, PERT, POW, EXACT) make_wpencil_set<NGL, EulerTheta<3, PERT, POW>, EXACT>(JX_EQ_EULER_THETA, PERT, POW)
+#define JX_WROW(NGL) \
+    JX_WSET(NGL, false, false, true), JX_WSET(NGL, false, true, true), JX_WSET(NGL, true, false, true), \
+    JX_WSET(NGL, true, true, true), JX_WSET(NGL, false, false, false), JX_WSET(NGL, false, true, false), \
+    JX_WSET(NGL, true, false, false), JX_WSET(NGL, true, true, false)
+
 const KernelSet *lookup_euler_theta_3d(int ngl, int lpert, int jxpow, int lvisc, int variant) {
-    static const KernelSet table[] = {JX_ROW(3), JX_ROW(5), JX_ROW(6), JX_ROW(8)};
+    static const KernelSet table[] = {JX_ROW(3), JX_ROW(5), JX_ROW(6), JX_ROW(8), JX_PROW(3), JX_PROW(5), JX_WROW(3), JX_WROW(5), JX_WROW(6)};
     for (const KernelSet &k : table)
         if (k.ngl == ngl && k.lpert == lpert && k.jxpow == jxpow && k.lvisc == lvisc && k.variant == variant) return &k;
     return nullptr;

@@ -14,6 +14,7 @@ struct KernelSet {
     int nsd, ngl, eq_id, lpert, jxpow, lvisc, variant;
     int neq;
     int elems_per_block;
+    int rec_layout;                                             // element-record layout the kernel reads (RetileArgs::layout)
     int nthreads;
     size_t smem_bytes;
     cudaError_t (*prepare)();                                   // cudaFuncSetAttribute(s)
@@ -21,6 +22,7 @@ struct KernelSet {
     void (*launch_elem)(const ElemArgs &, int grid, cudaStream_t);
     void (*launch_bc)(const BcArgs &, cudaStream_t);
     void (*launch_gather)(const GatherArgs &, cudaStream_t);
+    void (*launch_aux)(const AuxArgs &, int grid, cudaStream_t);   // nullptr unless the element kernel reads ElemArgs::aux
 };
 
 // each instantiation unit exports one lookup; returns nullptr if it does not hold the combination

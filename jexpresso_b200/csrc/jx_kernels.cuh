@@ -71,7 +71,25 @@ struct RetileArgs {
     int64_t nelem;
     int nsd, ngl, np, nmet, npp, rec_bytes;
     int slot;                 // metric slot; nmet-1 = Je (stored as ωJac); -1 = connectivity
+    int layout;               // 0: met[slot][node]; 1: pencil streams (3D, see k_elem_pencil)
 };
+
+// Record layout 1 (3D, pencil kernel): the metric doubles of one element are stored in the order the
+// pencil kernel's threads consume them, so that every load instruction of a warp is one contiguous run.
+// Thread c in [0,n^2) owns the xi-pencil (j,k)=(c%n,c/n), the eta-pencil (i,k)=(c%n,c/n) and the
+// zeta-pencil (i,j)=(c%n,c/n); stream s of thread c sits at rec[s*n^2 + c]:
+//   s = q*n + m        (q=0..2)  d(xi)/d(x,y,z)   at node m of the xi-pencil
+//   s = 3n + q*n + m             d(eta)/d(x,y,z)  at node m of the eta-pencil
+//   s = 6n + q*n + m             d(zeta)/d(x,y,z) at node m of the zeta-pencil
+//   s = 9n + m                   ωJac             at node m of the zeta-pencil
+__host__ __device__ inline int pencil_stream_index(int n, int slot, int l) {
+    const int i = l % n, j = (l / n) % n, k = l / (n * n);
+    const int nc = n * n;
+    if (slot < 3) return (slot * n + i) * nc + (j + n * k);
+    if (slot < 6) return (3 * n + (slot - 3) * n + j) * nc + (i + n * k);
+    if (slot < 9) return (6 * n + (slot - 6) * n + k) * nc + (i + n * j);
+    return (9 * n + k) * nc + (i + n * j);
+}
 
 // element-fastest Julia arrays [E, n, n, n] -> per-element records; thread = (element, local node)
 static __global__ void k_retile(RetileArgs a) {
@@ -89,7 +107,7 @@ static __global__ void k_retile(RetileArgs a) {
         if (l == 0)
             for (int p = a.np; p < a.npp; ++p) rc[p] = 0;
     } else if (a.slot < a.nmet - 1) {
-        rm[a.slot * a.np + l] = a.src[src];
+        rm[a.layout == 1 ? pencil_stream_index(n, a.slot, l) : a.slot * a.np + l] = a.src[src];
     } else {
         const double Je = a.src[src];
         double wJ;
@@ -101,7 +119,7 @@ static __global__ void k_retile(RetileArgs a) {
             const int i = l % n, j = l / n;
             wJ = a.omega[i] * a.omega[j] * Je;               // rhs.jl:1515-1516
         }
-        rm[(a.nmet - 1) * a.np + l] = wJ;
+        rm[a.layout == 1 ? pencil_stream_index(n, a.nmet - 1, l) : (a.nmet - 1) * a.np + l] = wJ;
     }
 }
 
@@ -190,6 +208,7 @@ struct ElemArgs {
     double *du;            // atomics mode target
     const double *Minv;
     const double *coords;  // [nsd][npoin] (only read by functors with NEEDS_XYZ)
+    const double *aux;     // [npoin] per-node part of the flux (k_node_aux), kernels with EQ::HAS_AUX only
     const int32_t *elist;  // optional element subset (interface / interior split); nullptr = all
     int64_t nelem, npoin;  // nelem = number of elements this launch processes
     int atomics;
@@ -446,6 +465,495 @@ k_elem_node(const __grid_constant__ ElemArgs a) {
             }
         }
         __syncthreads();   // all reads of this buffer / flux tiles done before they are refilled
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused per-element kernel, variant "pencil" (3D, inviscid): the same arithmetic as k_elem_node,
+// re-tiled for the measured B200 limits.  A warp-wide LDS.64 costs 2 cycles (256 B through the
+// 128 B/clk shared-memory return path, broadcast or not -- scripts/micro/micro.cu) against 0.5 cycle
+// for a warp-wide DFMA, so the one-thread-per-node form (one shared load per FMA) is bound by shared
+// memory, not by FP64 or HBM (profiles/r01a).  Here every derivative direction is computed by the
+// thread that owns the whole LGL line ("pencil") in that direction: n loads feed n*n FMAs, and the
+// dψ entries are compile-time constant-bank operands.  Thread c of an element owns
+//     xi-pencil (j,k)=(c%n,c/n)   eta-pencil (i,k)=(c%n,c/n)   zeta-pencil (i,j)=(c%n,c/n)
+// and keeps the three metric terms of each of its pencils in registers for all equations (record
+// layout 1, pencil_stream_index).  Per equation:
+//     xi pass   : a_F = dF/dξ·ξx, a_G = dG/dξ·ξy, a_H = dH/dξ·ξz            -> shared partials
+//     eta pass  : a_F += dF/dη·ηx, ...                                     (in place)
+//     zeta pass : dFdx = a_F + dF/dζ·ζx, ...; rhs = 0 - ωJ((dFdx+dGdy+dHdz) - S)
+// which is exactly the left-to-right order of rhs.jl:1679-1696, so EXACT=true is bit-identical to
+// k_elem_node and to the oracle.  EXACT=false carries one partial (the sum over F,G,H) instead of
+// three: 1/3 less shared-memory traffic, sums associated differently (within the 1e-12 parity bar).
+// Records are streamed straight into registers (each double is used by exactly one thread); the
+// next group's records are pulled into L2 one iteration ahead with cp.async.bulk.prefetch.L2.
+// ------------------------------------------------------------------------------------------
+template <int NGL, class EQ, int EPB, bool EXACT>
+struct ElemPencilCfg {
+    static constexpr int N = NGL, NC = NGL * NGL, NP = NGL * NGL * NGL, NEQ = EQ::NEQ;
+    static constexpr int NT = round_up(EPB * NC, 32);
+    static constexpr int NPART = EXACT ? 3 : 1;
+    static constexpr int FLD_D = 3 * NEQ * NP;       // F,G,H of every equation at every node
+    static constexpr int PART_D = 2 * NPART * NP;    // partial sums, double buffered by equation parity
+    static constexpr size_t SMEM_BYTES = (size_t)EPB * (FLD_D + PART_D) * 8;
+};
+
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+template <int NGL, class EQ, int EPB, bool EXACT>
+static __global__ void __launch_bounds__(ElemPencilCfg<NGL, EQ, EPB, EXACT>::NT, 2)
+k_elem_pencil(const __grid_constant__ ElemArgs a) {
+    using C = ElemPencilCfg<NGL, EQ, EPB, EXACT>;
+    using G = Geo<3, NGL>;
+    constexpr int N = NGL, NC = C::NC, NP = C::NP, NEQ = C::NEQ, NPART = C::NPART, REC_BYTES = G::REC_BYTES;
+    static_assert(EQ::SRC_EQ >= -1, "pencil kernel keeps at most one source component in registers");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sm = reinterpret_cast<double *>(smem_raw);
+
+    const int t = threadIdx.x;
+    const bool active = t < EPB * NC;
+    const int slot = active ? t / NC : 0;
+    const int c = active ? t % NC : 0;
+    const int c0 = c % N, c1 = c / N;
+    double *X = sm + (size_t)slot * (C::FLD_D + C::PART_D);   // [3*NEQ][NP], node l = i + N*(j + N*k)
+    double *Pp = X + C::FLD_D;                                // [2][NPART][NP]
+    const int bx = N * c;              // xi-pencil:   node(m) = bx + m
+    const int by = c0 + NC * c1;       // eta-pencil:  node(m) = by + N*m
+    const int bz = c;                  // zeta-pencil: node(m) = bz + NC*m
+#define JX_D(m, i) a.dpsi[(m) + NGL * (i)]
+
+    const int64_t ngroups = (a.nelem + EPB - 1) / EPB;
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        {   // pull the next group's records towards L2 while this one computes
+            const int64_t pn = (g + gridDim.x) * EPB + t;
+            if (t < EPB && pn < a.nelem) {
+                const int64_t en = a.elist ? (int64_t)a.elist[pn] : pn;
+                prefetch_l2_bulk(a.rec + (size_t)en * REC_BYTES, REC_BYTES);
+            }
+        }
+        const int64_t pos = g * EPB + slot;
+        const bool live = active && pos < a.nelem;
+        const int64_t iel = live ? (a.elist ? (int64_t)a.elist[pos] : pos) : 0;
+        const double *rec = reinterpret_cast<const double *>(a.rec + (size_t)iel * REC_BYTES);
+        const int32_t *conn = reinterpret_cast<const int32_t *>(rec + G::NMET * NP);
+
+        double mx[3][N], my[3][N], mz[3][N], wj[N], mi[N], Ssrc[N];
+        int ip[N];
+        if (live) {
+#pragma unroll
+            for (int m = 0; m < N; ++m) ip[m] = __ldcs(conn + bz + NC * m);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int m = 0; m < N; ++m) {
+                    mx[q][m] = __ldcs(rec + (q * N + m) * NC + c);
+                    my[q][m] = __ldcs(rec + (3 * N + q * N + m) * NC + c);
+                    mz[q][m] = __ldcs(rec + (6 * N + q * N + m) * NC + c);
+                }
+#pragma unroll
+            for (int m = 0; m < N; ++m) wj[m] = __ldcs(rec + (9 * N + m) * NC + c);
+            // flux / source at the nodes of the zeta-pencil
+#pragma unroll
+            for (int m = 0; m < N; ++m) {
+                const int64_t node = ip[m];
+                double q[NEQ], qe[NEQ + 1], f[NEQ], gg[NEQ], h[NEQ];
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e) q[e] = __ldg(a.u + (size_t)e * a.npoin + node);
+#pragma unroll
+                for (int e = 0; e <= NEQ; ++e) qe[e] = EQ::NEEDS_QE ? __ldg(a.qe + (size_t)e * a.npoin + node) : 0.0;
+                EQ::flux(a.phys, q, qe, f, gg, h);
+                const int l = bz + NC * m;
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e) {
+                    X[(0 * NEQ + e) * NP + l] = f[e];
+                    X[(1 * NEQ + e) * NP + l] = gg[e];
+                    X[(2 * NEQ + e) * NP + l] = h[e];
+                }
+                Ssrc[m] = 0.0;
+                if constexpr (EQ::SRC_EQ >= 0) {
+                    if (a.lsource) {
+                        double xyz[3] = {0.0, 0.0, 0.0}, S[NEQ];
+                        if constexpr (EQ::NEEDS_XYZ) {
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) xyz[d] = __ldg(a.coords + (size_t)d * a.npoin + node);
+                        }
+                        EQ::source(a.phys, q, qe, xyz, S);
+                        Ssrc[m] = S[EQ::SRC_EQ >= 0 ? EQ::SRC_EQ : 0];
+                    }
+                }
+                mi[m] = (a.atomics && a.Minv) ? __ldg(a.Minv + node) : 1.0;
+            }
+        }
+        __syncthreads();
+
+#pragma unroll 1
+        for (int e = 0; e < NEQ; ++e) {
+            double *Pe = Pp + (e & 1) * NPART * NP;
+            const double *Fe = X + (0 * NEQ + e) * NP, *Ge = X + (1 * NEQ + e) * NP, *He = X + (2 * NEQ + e) * NP;
+            if (live) {   // xi pass
+                double f[N], gg[N], h[N];
+#pragma unroll
+                for (int m = 0; m < N; ++m) { f[m] = Fe[bx + m]; gg[m] = Ge[bx + m]; h[m] = He[bx + m]; }
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    double dF = 0, dG = 0, dH = 0;
+#pragma unroll
+                    for (int m = 0; m < N; ++m) {
+                        dF = fma(JX_D(m, i), f[m], dF);
+                        dG = fma(JX_D(m, i), gg[m], dG);
+                        dH = fma(JX_D(m, i), h[m], dH);
+                    }
+                    if constexpr (EXACT) {
+                        Pe[0 * NP + bx + i] = dF * mx[0][i];
+                        Pe[1 * NP + bx + i] = dG * mx[1][i];
+                        Pe[2 * NP + bx + i] = dH * mx[2][i];
+                    } else {
+                        Pe[bx + i] = (dF * mx[0][i] + dG * mx[1][i]) + dH * mx[2][i];
+                    }
+                }
+            }
+            __syncthreads();
+            if (live) {   // eta pass
+                double f[N], gg[N], h[N];
+#pragma unroll
+                for (int m = 0; m < N; ++m) { f[m] = Fe[by + N * m]; gg[m] = Ge[by + N * m]; h[m] = He[by + N * m]; }
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    double dF = 0, dG = 0, dH = 0;
+#pragma unroll
+                    for (int m = 0; m < N; ++m) {
+                        dF = fma(JX_D(m, j), f[m], dF);
+                        dG = fma(JX_D(m, j), gg[m], dG);
+                        dH = fma(JX_D(m, j), h[m], dH);
+                    }
+                    const int o = by + N * j;
+                    if constexpr (EXACT) {
+                        Pe[0 * NP + o] = Pe[0 * NP + o] + dF * my[0][j];
+                        Pe[1 * NP + o] = Pe[1 * NP + o] + dG * my[1][j];
+                        Pe[2 * NP + o] = Pe[2 * NP + o] + dH * my[2][j];
+                    } else {
+                        Pe[o] = Pe[o] + ((dF * my[0][j] + dG * my[1][j]) + dH * my[2][j]);
+                    }
+                }
+            }
+            __syncthreads();
+            if (live) {   // zeta pass + output
+                double f[N], gg[N], h[N];
+#pragma unroll
+                for (int m = 0; m < N; ++m) { f[m] = Fe[bz + NC * m]; gg[m] = Ge[bz + NC * m]; h[m] = He[bz + NC * m]; }
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    double dF = 0, dG = 0, dH = 0;
+#pragma unroll
+                    for (int m = 0; m < N; ++m) {
+                        dF = fma(JX_D(m, k), f[m], dF);
+                        dG = fma(JX_D(m, k), gg[m], dG);
+                        dH = fma(JX_D(m, k), h[m], dH);
+                    }
+                    const int o = bz + NC * k;
+                    double r;
+                    if constexpr (EXACT) {
+                        const double dFdx = Pe[0 * NP + o] + dF * mz[0][k];
+                        const double dGdy = Pe[1 * NP + o] + dG * mz[1][k];
+                        const double dHdz = Pe[2 * NP + o] + dH * mz[2][k];
+                        r = (dFdx + dGdy) + dHdz;
+                    } else {
+                        r = Pe[o] + ((dF * mz[0][k] + dG * mz[1][k]) + dH * mz[2][k]);
+                    }
+                    const double S = (e == EQ::SRC_EQ) ? Ssrc[k] : 0.0;
+                    const double out = 0.0 - wj[k] * (r - S);
+                    if (!a.atomics) a.rhs_el[((size_t)iel * NEQ + e) * NP + o] = out;
+                    else atomicAdd(&a.du[(size_t)e * a.npoin + ip[k]], out * mi[k]);
+                }
+            }
+        }
+        __syncthreads();   // all pencils done with X before the next group's fluxes overwrite it
+    }
+#undef JX_D
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-unique-node pre-pass of the pencil kernels: the part of user_flux! that depends on the node
+// only (the equation of state, one pow per node) is evaluated once per node instead of once per
+// element-node (x1.95 at nop=4), and -- in atomics mode -- the scatter target is zeroed in the same
+// sweep (replaces the memset).  Runs after the Dirichlet projection, like the flux evaluation it feeds.
+// ------------------------------------------------------------------------------------------
+struct AuxArgs {
+    const double *u, *qe;
+    double *aux;
+    double *zero;     // du to clear (atomics mode) or nullptr
+    int64_t npoin;
+    Phys phys;
+};
+
+template <class EQ>
+static __global__ void k_node_aux(const __grid_constant__ AuxArgs a) {
+    constexpr int NEQ = EQ::NEQ;
+    for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < a.npoin; ip += (int64_t)gridDim.x * blockDim.x) {
+        double q[NEQ], qe[NEQ + 1];
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) q[e] = ((EQ::AUX_MASK >> e) & 1u) ? a.u[(size_t)e * a.npoin + ip] : 0.0;
+#pragma unroll
+        for (int e = 0; e <= NEQ; ++e) qe[e] = (EQ::NEEDS_QE && ((EQ::AUX_MASK >> e) & 1u)) ? a.qe[(size_t)e * a.npoin + ip] : 0.0;
+        if constexpr (EQ::HAS_AUX) a.aux[ip] = EQ::aux(a.phys, q, qe);
+        if (a.zero) {
+#pragma unroll
+            for (int e = 0; e < NEQ; ++e) a.zero[(size_t)e * a.npoin + ip] = 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused per-element kernel, variant "wpencil" (3D, inviscid): the pencil kernel with ONE element per
+// CTA of round_up(n^2,32) threads (one warp at nop=4), many small CTAs per SM.  profiles/r01b showed the
+// 5-elements-per-128-threads pencil kernel latency bound at 2 warps per scheduler: 11 block barriers per
+// group couple all its warps, and the global-load phase of a group is exposed.  Here no barrier is wider
+// than one element, so 9-10 independent warps per SM overlap each other's load, flux and pencil phases.
+// The flux phase runs node-parallel over all 32 lanes; the pencil passes use n^2 of them.
+// ------------------------------------------------------------------------------------------
+#define JX_WPENCIL_MAXREG 224   // 9 one-warp CTAs per SM at nop=4 (shared memory allows 10)
+template <int NGL, class EQ, bool EXACT>
+struct ElemWPencilCfg {
+    static constexpr int N = NGL, NC = NGL * NGL, NP = NGL * NGL * NGL, NEQ = EQ::NEQ;
+    static constexpr int NT = round_up(NC, 32);
+    static constexpr int NPART = EXACT ? 3 : 1;
+    static constexpr int NPD = round_up(NP, 2);
+    static constexpr int FLD_D = 3 * NEQ * NP;
+    static constexpr int PART_D = NPART * NP;
+    static constexpr int D_TOTAL = round_up(FLD_D + PART_D + 2 * NP, 2);      // + source field + M^-1 field
+    static constexpr size_t SMEM_BYTES = (size_t)D_TOTAL * 8 + (size_t)round_up(NP, 4) * 4;   // + node ids
+};
+
+template <int NGL, class EQ, bool EXACT>
+static __global__ void __maxnreg__(JX_WPENCIL_MAXREG)
+k_elem_wpencil(const __grid_constant__ ElemArgs a) {
+    using C = ElemWPencilCfg<NGL, EQ, EXACT>;
+    using G = Geo<3, NGL>;
+    constexpr int N = NGL, NC = C::NC, NP = C::NP, NEQ = C::NEQ, REC_BYTES = G::REC_BYTES, NT = C::NT;
+    constexpr int R = (NP + NT - 1) / NT;          // flux rounds: node l = r*NT + t
+    constexpr int RB = EQ::NEEDS_QE ? (R > 2 ? 2 : R) : R;   // rounds whose gathers are in flight together
+    static_assert(EQ::SRC_EQ >= -1, "pencil kernels keep at most one source component");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *X = reinterpret_cast<double *>(smem_raw);     // [3*NEQ][NP]
+    double *Pe = X + C::FLD_D;                            // [NPART][NP]
+    double *Sf = Pe + C::PART_D;                          // [NP] source of equation SRC_EQ
+    double *Mf = Sf + NP;                                 // [NP] M^-1 (atomics mode with folding) or 1
+    int32_t *sIp = reinterpret_cast<int32_t *>(X + C::D_TOTAL);
+
+    const int t = threadIdx.x;
+    const bool pl = t < NC;            // pencil lane
+    const int c = pl ? t : 0;
+    const int c0 = c % N, c1 = c / N;
+    const int bx = N * c, by = c0 + NC * c1, bz = c;
+    const bool fold = a.atomics && a.Minv != nullptr;
+#define JX_D(m, i) a.dpsi[(m) + NGL * (i)]
+    auto rec_of = [&](int64_t p) -> const double * {
+        return reinterpret_cast<const double *>(a.rec + (size_t)(a.elist ? (int64_t)a.elist[p] : p) * REC_BYTES);
+    };
+
+    // node ids of the first element; inside the loop they are fetched one element ahead
+    int ndn[R];
+    if ((int64_t)blockIdx.x < a.nelem) {
+        const int32_t *cn = reinterpret_cast<const int32_t *>(rec_of(blockIdx.x) + G::NMET * NP);
+#pragma unroll
+        for (int r = 0; r < R; ++r) ndn[r] = (r * NT + t < NP) ? __ldcs(cn + r * NT + t) : 0;
+    }
+    for (int64_t pos = blockIdx.x; pos < a.nelem; pos += gridDim.x) {
+        const int64_t pn = pos + gridDim.x;
+        const int64_t iel = a.elist ? (int64_t)a.elist[pos] : pos;
+        const double *rec = rec_of(pos);
+        int nd[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) nd[r] = ndn[r];
+
+        // metric terms of this thread's three pencils -> registers (in flight during the flux phase)
+        double mx[3][N], my[3][N], mz[3][N], wj[N];
+        if (pl) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int m = 0; m < N; ++m) {
+                    mx[q][m] = __ldcs(rec + (q * N + m) * NC + c);
+                    my[q][m] = __ldcs(rec + (3 * N + q * N + m) * NC + c);
+                    mz[q][m] = __ldcs(rec + (6 * N + q * N + m) * NC + c);
+                }
+#pragma unroll
+            for (int m = 0; m < N; ++m) wj[m] = __ldcs(rec + (9 * N + m) * NC + c);
+        }
+        if (pn < a.nelem) {   // next element: node ids -> registers, record -> L2
+            const double *rn = rec_of(pn);
+            const int32_t *cn = reinterpret_cast<const int32_t *>(rn + G::NMET * NP);
+#pragma unroll
+            for (int r = 0; r < R; ++r) ndn[r] = (r * NT + t < NP) ? __ldcs(cn + r * NT + t) : 0;
+            if (t == 0) prefetch_l2_bulk(rn, REC_BYTES);
+        }
+        // flux / source at every node, node-parallel; the gathers of RB rounds are issued together
+#pragma unroll
+        for (int rb = 0; rb < R; rb += RB) {
+            double q[RB][NEQ], qe[RB][NEQ + 1], ax[RB], mv[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int l = (rb + r) * NT + t;
+                const int64_t node = nd[(rb + r) < R ? (rb + r) : 0];
+                const bool on = (rb + r) < R && l < NP;
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e) q[r][e] = on ? __ldg(a.u + (size_t)e * a.npoin + node) : 1.0;
+#pragma unroll
+                for (int e = 0; e <= NEQ; ++e) qe[r][e] = (EQ::NEEDS_QE && on) ? __ldg(a.qe + (size_t)e * a.npoin + node) : 0.0;
+                if constexpr (EQ::HAS_AUX) ax[r] = on ? __ldg(a.aux + node) : 1.0;
+                mv[r] = (fold && on) ? __ldg(a.Minv + node) : 1.0;
+            }
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int l = (rb + r) * NT + t;
+                if ((rb + r) < R && l < NP) {
+                    const int64_t node = nd[(rb + r) < R ? (rb + r) : 0];
+                    double f[NEQ], gg[NEQ], h[NEQ];
+                    if constexpr (EQ::HAS_AUX) EQ::flux_aux(a.phys, q[r], qe[r], ax[r], f, gg, h);
+                    else EQ::flux(a.phys, q[r], qe[r], f, gg, h);
+#pragma unroll
+                    for (int e = 0; e < NEQ; ++e) {
+                        X[(0 * NEQ + e) * NP + l] = f[e];
+                        X[(1 * NEQ + e) * NP + l] = gg[e];
+                        X[(2 * NEQ + e) * NP + l] = h[e];
+                    }
+                    if constexpr (EQ::SRC_EQ >= 0) {
+                        double sv = 0.0;
+                        if (a.lsource) {
+                            double xyz[3] = {0.0, 0.0, 0.0}, S[NEQ];
+                            if constexpr (EQ::NEEDS_XYZ) {
+#pragma unroll
+                                for (int d = 0; d < 3; ++d) xyz[d] = __ldg(a.coords + (size_t)d * a.npoin + node);
+                            }
+                            EQ::source(a.phys, q[r], qe[r], xyz, S);
+                            sv = S[EQ::SRC_EQ >= 0 ? EQ::SRC_EQ : 0];
+                        }
+                        Sf[l] = sv;
+                    }
+                    Mf[l] = mv[r];
+                    sIp[l] = (int32_t)node;
+                }
+            }
+        }
+        __syncthreads();
+
+#pragma unroll 1
+        for (int e = 0; e < NEQ; ++e) {
+            const double *Fe = X + (0 * NEQ + e) * NP, *Ge = X + (1 * NEQ + e) * NP, *He = X + (2 * NEQ + e) * NP;
+            if (pl) {   // xi pass
+                double f[N], gg[N], h[N];
+#pragma unroll
+                for (int m = 0; m < N; ++m) { f[m] = Fe[bx + m]; gg[m] = Ge[bx + m]; h[m] = He[bx + m]; }
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    double dF = 0, dG = 0, dH = 0;
+#pragma unroll
+                    for (int m = 0; m < N; ++m) {
+                        dF = fma(JX_D(m, i), f[m], dF);
+                        dG = fma(JX_D(m, i), gg[m], dG);
+                        dH = fma(JX_D(m, i), h[m], dH);
+                    }
+                    if constexpr (EXACT) {
+                        Pe[0 * NP + bx + i] = dF * mx[0][i];
+                        Pe[1 * NP + bx + i] = dG * mx[1][i];
+                        Pe[2 * NP + bx + i] = dH * mx[2][i];
+                    } else {
+                        Pe[bx + i] = (dF * mx[0][i] + dG * mx[1][i]) + dH * mx[2][i];
+                    }
+                }
+            }
+            __syncthreads();
+            if (pl) {   // eta pass
+                double f[N], gg[N], h[N];
+#pragma unroll
+                for (int m = 0; m < N; ++m) { f[m] = Fe[by + N * m]; gg[m] = Ge[by + N * m]; h[m] = He[by + N * m]; }
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    double dF = 0, dG = 0, dH = 0;
+#pragma unroll
+                    for (int m = 0; m < N; ++m) {
+                        dF = fma(JX_D(m, j), f[m], dF);
+                        dG = fma(JX_D(m, j), gg[m], dG);
+                        dH = fma(JX_D(m, j), h[m], dH);
+                    }
+                    const int o = by + N * j;
+                    if constexpr (EXACT) {
+                        Pe[0 * NP + o] = Pe[0 * NP + o] + dF * my[0][j];
+                        Pe[1 * NP + o] = Pe[1 * NP + o] + dG * my[1][j];
+                        Pe[2 * NP + o] = Pe[2 * NP + o] + dH * my[2][j];
+                    } else {
+                        Pe[o] = Pe[o] + ((dF * my[0][j] + dG * my[1][j]) + dH * my[2][j]);
+                    }
+                }
+            }
+            __syncthreads();
+            if (pl) {   // zeta pass + output
+                double f[N], gg[N], h[N];
+#pragma unroll
+                for (int m = 0; m < N; ++m) { f[m] = Fe[bz + NC * m]; gg[m] = Ge[bz + NC * m]; h[m] = He[bz + NC * m]; }
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    double dF = 0, dG = 0, dH = 0;
+#pragma unroll
+                    for (int m = 0; m < N; ++m) {
+                        dF = fma(JX_D(m, k), f[m], dF);
+                        dG = fma(JX_D(m, k), gg[m], dG);
+                        dH = fma(JX_D(m, k), h[m], dH);
+                    }
+                    const int o = bz + NC * k;
+                    double r;
+                    if constexpr (EXACT) {
+                        const double dFdx = Pe[0 * NP + o] + dF * mz[0][k];
+                        const double dGdy = Pe[1 * NP + o] + dG * mz[1][k];
+                        const double dHdz = Pe[2 * NP + o] + dH * mz[2][k];
+                        r = (dFdx + dGdy) + dHdz;
+                    } else {
+                        r = Pe[o] + ((dF * mz[0][k] + dG * mz[1][k]) + dH * mz[2][k]);
+                    }
+                    double S = 0.0;
+                    if constexpr (EQ::SRC_EQ >= 0) {
+                        if (e == EQ::SRC_EQ) S = Sf[o];
+                    }
+                    const double out = 0.0 - wj[k] * (r - S);
+                    if (!a.atomics) a.rhs_el[((size_t)iel * NEQ + e) * NP + o] = out;
+                    else atomicAdd(&a.du[(size_t)e * a.npoin + sIp[o]], out * Mf[o]);
+                }
+            }
+            __syncthreads();   // partials (and, after the last equation, the fields) are free again
+        }
+    }
+#undef JX_D
+}
+
+// ------------------------------------------------------------------------------------------
+// self test of Recip::div against the compiler's correctly rounded `/` (jx_selftest(ctx, 0, n, &bad)).
+// Samples: b = density-like values in [1e-3, 1e3] and wide-range values, a = momentum-like values of
+// both signs, exact zeros, powers of two and near-overflow / near-underflow magnitudes.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t jx_mix64(uint64_t x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+static __global__ void k_selftest_div(int64_t n, uint64_t seed, unsigned long long *bad) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t h1 = jx_mix64(seed + 2 * (uint64_t)i), h2 = jx_mix64(seed + 2 * (uint64_t)i + 1);
+        // mantissas from the hash, exponents from a small menu
+        const int mode = (int)(h1 & 7);
+        const int eb = mode < 5 ? (int)((h2 >> 52) % 21) - 10 : (int)((h2 >> 52) % 1200) - 600;
+        const int ea = mode < 5 ? (int)((h1 >> 52) % 41) - 20 : (int)((h1 >> 52) % 1800) - 900;
+        double b = __longlong_as_double((long long)((h2 & 0x000fffffffffffffull) | ((uint64_t)(1023 + eb) << 52)));
+        double a = __longlong_as_double((long long)((h1 >> 3 & 0x000fffffffffffffull) | ((uint64_t)(1023 + ea) << 52)));
+        if (h1 & 8) a = -a;
+        if (mode == 6 && (h2 & 16)) b = -b;
+        if ((h1 >> 4 & 63) == 0) a = 0.0;
+        if ((h1 >> 10 & 63) == 0) a = ldexp(1.0, ea);
+        const Recip rc(b);
+        const double q1 = rc.div(a), q2 = a / b;
+        if (__double_as_longlong(q1) != __double_as_longlong(q2) && !(q1 != q1 && q2 != q2)) atomicAdd(bad, 1ull);
     }
 }
 

@@ -34,6 +34,12 @@ void launch_bc_t(const BcArgs &a, cudaStream_t s) {
     k_bc_dirichlet<EQ><<<(a.nb + 127) / 128, 128, 0, s>>>(a);
 }
 
+template <class EQ>
+void launch_aux_t(const AuxArgs &a, int grid, cudaStream_t s) {
+    if (a.npoin <= 0) return;
+    k_node_aux<EQ><<<grid, 256, 0, s>>>(a);
+}
+
 template <int NEQ>
 void launch_gather_t(const GatherArgs &a, cudaStream_t s) {
     if (a.npoin <= 0) return;
@@ -47,6 +53,7 @@ KernelSet make_node_set(int eq_id, int lpert, int jxpow) {
     ks.nsd = NSD; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = VISC; ks.variant = 0;
     ks.neq = EQ::NEQ;
     ks.elems_per_block = K::EPB;
+    ks.rec_layout = 0;
     ks.nthreads = K::C::NT;
     ks.smem_bytes = K::C::SMEM_BYTES;
     ks.prepare = &K::prepare;
@@ -54,6 +61,83 @@ KernelSet make_node_set(int eq_id, int lpert, int jxpow) {
     ks.launch_elem = &K::launch;
     ks.launch_bc = &launch_bc_t<EQ>;
     ks.launch_gather = &launch_gather_t<EQ::NEQ>;
+    ks.launch_aux = nullptr;
+    return ks;
+}
+
+// variant 1 (EXACT) / 2 (single partial): pencil kernel, 3D inviscid
+template <int NGL, class EQ, bool EXACT>
+struct PencilKernel {
+    static constexpr int NC = NGL * NGL;
+    static constexpr int EPB = NC >= 128 ? 1 : (128 / NC);
+    using C = ElemPencilCfg<NGL, EQ, EPB, EXACT>;
+    static cudaError_t prepare() {
+        return cudaFuncSetAttribute(k_elem_pencil<NGL, EQ, EPB, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)C::SMEM_BYTES);
+    }
+    static int max_blocks() {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_pencil<NGL, EQ, EPB, EXACT>, C::NT, C::SMEM_BYTES);
+        return nb;
+    }
+    static void launch(const ElemArgs &a, int grid, cudaStream_t s) {
+        k_elem_pencil<NGL, EQ, EPB, EXACT><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+    }
+};
+
+template <int NGL, class EQ, bool EXACT>
+KernelSet make_pencil_set(int eq_id, int lpert, int jxpow) {
+    using K = PencilKernel<NGL, EQ, EXACT>;
+    KernelSet ks;
+    ks.nsd = 3; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = 0; ks.variant = EXACT ? 1 : 2;
+    ks.neq = EQ::NEQ;
+    ks.elems_per_block = K::EPB;
+    ks.rec_layout = 1;
+    ks.nthreads = K::C::NT;
+    ks.smem_bytes = K::C::SMEM_BYTES;
+    ks.prepare = &K::prepare;
+    ks.max_blocks_per_sm = &K::max_blocks;
+    ks.launch_elem = &K::launch;
+    ks.launch_bc = &launch_bc_t<EQ>;
+    ks.launch_gather = &launch_gather_t<EQ::NEQ>;
+    ks.launch_aux = nullptr;
+    return ks;
+}
+
+// variant 3 (EXACT) / 4 (single partial): one element per CTA pencil kernel, 3D inviscid
+template <int NGL, class EQ, bool EXACT>
+struct WPencilKernel {
+    using C = ElemWPencilCfg<NGL, EQ, EXACT>;
+    static cudaError_t prepare() {
+        return cudaFuncSetAttribute(k_elem_wpencil<NGL, EQ, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)C::SMEM_BYTES);
+    }
+    static int max_blocks() {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_wpencil<NGL, EQ, EXACT>, C::NT, C::SMEM_BYTES);
+        return nb;
+    }
+    static void launch(const ElemArgs &a, int grid, cudaStream_t s) {
+        k_elem_wpencil<NGL, EQ, EXACT><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+    }
+};
+
+template <int NGL, class EQ, bool EXACT>
+KernelSet make_wpencil_set(int eq_id, int lpert, int jxpow) {
+    using K = WPencilKernel<NGL, EQ, EXACT>;
+    KernelSet ks;
+    ks.nsd = 3; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = 0; ks.variant = EXACT ? 3 : 4;
+    ks.neq = EQ::NEQ;
+    ks.elems_per_block = 1;
+    ks.rec_layout = 1;
+    ks.nthreads = K::C::NT;
+    ks.smem_bytes = K::C::SMEM_BYTES;
+    ks.prepare = &K::prepare;
+    ks.max_blocks_per_sm = &K::max_blocks;
+    ks.launch_elem = &K::launch;
+    ks.launch_bc = &launch_bc_t<EQ>;
+    ks.launch_gather = &launch_gather_t<EQ::NEQ>;
+    ks.launch_aux = EQ::HAS_AUX ? &launch_aux_t<EQ> : nullptr;
     return ks;
 }
 
