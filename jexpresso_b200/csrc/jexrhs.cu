@@ -674,7 +674,7 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     ea.aux = nullptr;
     if (ks->launch_aux) {                                                // per-node flux ingredient (+ zero-fill of du)
         PhaseScope ps(c, PH_AUX);
-        if (!c->aux) { int rc = dalloc(c, &c->aux, (size_t)N); if (rc) return rc; }
+        if (!c->aux) { int rc = dalloc(c, &c->aux, (size_t)N * 4); if (rc) return rc; }   // up to 4 values per node
         AuxArgs aa;
         aa.u = u; aa.qe = c->qe; aa.aux = c->aux; aa.zero = atomics ? du : nullptr; aa.npoin = N; aa.phys = c->phys;
         ks->launch_aux(aa, (int)std::min<int64_t>((N + 255) / 256, (int64_t)c->num_sms * 8), s);

@@ -208,7 +208,7 @@ struct ElemArgs {
     double *du;            // atomics mode target
     const double *Minv;
     const double *coords;  // [nsd][npoin] (only read by functors with NEEDS_XYZ)
-    const double *aux;     // [npoin] per-node part of the flux (k_node_aux), kernels with EQ::HAS_AUX only
+    const double *aux;     // [NAUX][npoin] per-node part of the flux (k_node_aux), kernels with EQ::HAS_AUX only
     const int32_t *elist;  // optional element subset (interface / interior split); nullptr = all
     int64_t nelem, npoin;  // nelem = number of elements this launch processes
     int atomics;
@@ -682,7 +682,7 @@ k_elem_pencil(const __grid_constant__ ElemArgs a) {
 // ------------------------------------------------------------------------------------------
 struct AuxArgs {
     const double *u, *qe;
-    double *aux;
+    double *aux;      // [NAUX][npoin]
     double *zero;     // du to clear (atomics mode) or nullptr
     int64_t npoin;
     Phys phys;
@@ -696,8 +696,13 @@ static __global__ void k_node_aux(const __grid_constant__ AuxArgs a) {
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) q[e] = ((EQ::AUX_MASK >> e) & 1u) ? a.u[(size_t)e * a.npoin + ip] : 0.0;
 #pragma unroll
-        for (int e = 0; e <= NEQ; ++e) qe[e] = (EQ::NEEDS_QE && ((EQ::AUX_MASK >> e) & 1u)) ? a.qe[(size_t)e * a.npoin + ip] : 0.0;
-        if constexpr (EQ::HAS_AUX) a.aux[ip] = EQ::aux(a.phys, q, qe);
+        for (int e = 0; e <= NEQ; ++e) qe[e] = (EQ::NEEDS_QE && (e == NEQ || ((EQ::AUX_MASK >> e) & 1u))) ? a.qe[(size_t)e * a.npoin + ip] : 0.0;
+        if constexpr (EQ::HAS_AUX) {
+            double ax[EQ::NAUX > 0 ? EQ::NAUX : 1];
+            EQ::aux(a.phys, q, qe, ax);
+#pragma unroll
+            for (int x = 0; x < EQ::NAUX; ++x) a.aux[(size_t)x * a.npoin + ip] = ax[x];
+        }
         if (a.zero) {
 #pragma unroll
             for (int e = 0; e < NEQ; ++e) a.zero[(size_t)e * a.npoin + ip] = 0.0;
@@ -733,7 +738,7 @@ k_elem_wpencil(const __grid_constant__ ElemArgs a) {
     using G = Geo<3, NGL>;
     constexpr int N = NGL, NC = C::NC, NP = C::NP, NEQ = C::NEQ, REC_BYTES = G::REC_BYTES, NT = C::NT;
     constexpr int R = (NP + NT - 1) / NT;          // flux rounds: node l = r*NT + t
-    constexpr int RB = EQ::NEEDS_QE ? (R > 2 ? 2 : R) : R;   // rounds whose gathers are in flight together
+    constexpr int RB = (EQ::NEEDS_QE && !EQ::HAS_AUX) ? (R > 2 ? 2 : R) : R;   // rounds whose gathers are in flight together
     static_assert(EQ::SRC_EQ >= -1, "pencil kernels keep at most one source component");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *X = reinterpret_cast<double *>(smem_raw);     // [3*NEQ][NP]
@@ -792,17 +797,24 @@ k_elem_wpencil(const __grid_constant__ ElemArgs a) {
         // flux / source at every node, node-parallel; the gathers of RB rounds are issued together
 #pragma unroll
         for (int rb = 0; rb < R; rb += RB) {
-            double q[RB][NEQ], qe[RB][NEQ + 1], ax[RB], mv[RB];
+            constexpr int NAX = EQ::HAS_AUX ? EQ::NAUX : 1;
+            double q[RB][NEQ], qe[RB][NEQ + 1], ax[RB][NAX], mv[RB];
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
                 const int l = (rb + r) * NT + t;
                 const int64_t node = nd[(rb + r) < R ? (rb + r) : 0];
                 const bool on = (rb + r) < R && l < NP;
 #pragma unroll
-                for (int e = 0; e < NEQ; ++e) q[r][e] = on ? __ldg(a.u + (size_t)e * a.npoin + node) : 1.0;
+                for (int e = 0; e < NEQ; ++e) {
+                    const bool need = !EQ::HAS_AUX || ((EQ::FLUX_QMASK >> e) & 1u);
+                    q[r][e] = (on && need) ? __ldg(a.u + (size_t)e * a.npoin + node) : 1.0;
+                }
 #pragma unroll
-                for (int e = 0; e <= NEQ; ++e) qe[r][e] = (EQ::NEEDS_QE && on) ? __ldg(a.qe + (size_t)e * a.npoin + node) : 0.0;
-                if constexpr (EQ::HAS_AUX) ax[r] = on ? __ldg(a.aux + node) : 1.0;
+                for (int e = 0; e <= NEQ; ++e) qe[r][e] = (EQ::NEEDS_QE && !EQ::HAS_AUX && on) ? __ldg(a.qe + (size_t)e * a.npoin + node) : 0.0;
+                if constexpr (EQ::HAS_AUX) {
+#pragma unroll
+                    for (int x = 0; x < EQ::NAUX; ++x) ax[r][x] = on ? __ldg(a.aux + (size_t)x * a.npoin + node) : 1.0;
+                }
                 mv[r] = (fold && on) ? __ldg(a.Minv + node) : 1.0;
             }
 #pragma unroll
@@ -811,7 +823,7 @@ k_elem_wpencil(const __grid_constant__ ElemArgs a) {
                 if ((rb + r) < R && l < NP) {
                     const int64_t node = nd[(rb + r) < R ? (rb + r) : 0];
                     double f[NEQ], gg[NEQ], h[NEQ];
-                    if constexpr (EQ::HAS_AUX) EQ::flux_aux(a.phys, q[r], qe[r], ax[r], f, gg, h);
+                    if constexpr (EQ::HAS_AUX) EQ::flux_aux(a.phys, q[r], ax[r], f, gg, h);
                     else EQ::flux(a.phys, q[r], qe[r], f, gg, h);
 #pragma unroll
                     for (int e = 0; e < NEQ; ++e) {
@@ -822,13 +834,16 @@ k_elem_wpencil(const __grid_constant__ ElemArgs a) {
                     if constexpr (EQ::SRC_EQ >= 0) {
                         double sv = 0.0;
                         if (a.lsource) {
-                            double xyz[3] = {0.0, 0.0, 0.0}, S[NEQ];
-                            if constexpr (EQ::NEEDS_XYZ) {
+                            if constexpr (EQ::HAS_AUX) sv = EQ::source_aux(a.phys, q[r], ax[r]);
+                            else {
+                                double xyz[3] = {0.0, 0.0, 0.0}, S[NEQ];
+                                if constexpr (EQ::NEEDS_XYZ) {
 #pragma unroll
-                                for (int d = 0; d < 3; ++d) xyz[d] = __ldg(a.coords + (size_t)d * a.npoin + node);
+                                    for (int d = 0; d < 3; ++d) xyz[d] = __ldg(a.coords + (size_t)d * a.npoin + node);
+                                }
+                                EQ::source(a.phys, q[r], qe[r], xyz, S);
+                                sv = S[EQ::SRC_EQ >= 0 ? EQ::SRC_EQ : 0];
                             }
-                            EQ::source(a.phys, q[r], qe[r], xyz, S);
-                            sv = S[EQ::SRC_EQ >= 0 ? EQ::SRC_EQ : 0];
                         }
                         Sf[l] = sv;
                     }
