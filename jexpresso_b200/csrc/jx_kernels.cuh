@@ -718,18 +718,30 @@ static __global__ void k_node_aux(const __grid_constant__ AuxArgs a) {
 // than one element, so 9-10 independent warps per SM overlap each other's load, flux and pencil phases.
 // The flux phase runs node-parallel over all 32 lanes; the pencil passes use n^2 of them.
 // ------------------------------------------------------------------------------------------
-#define JX_WPENCIL_MAXREG 224   // 9 one-warp CTAs per SM at nop=4 (shared memory allows 10)
+#define JX_WPENCIL_MAXREG 224   // 9 one-warp CTAs per SM at nop=4
+#ifndef JX_WPENCIL_STAGE
+#define JX_WPENCIL_STAGE 0       // 1: gather q/aux of the next element with cp.async into shared staging (measured slower, profiles/r01e)
+#endif
 template <int NGL, class EQ, bool EXACT>
 struct ElemWPencilCfg {
     static constexpr int N = NGL, NC = NGL * NGL, NP = NGL * NGL * NGL, NEQ = EQ::NEQ;
     static constexpr int NT = round_up(NC, 32);
     static constexpr int NPART = EXACT ? 3 : 1;
-    static constexpr int NPD = round_up(NP, 2);
+    static constexpr int R = (NP + NT - 1) / NT;                 // flux rounds: node l = r*NT + t
+    static constexpr int NQ = EQ::NEQ - (EQ::FLUX_QMASK == ((1u << (EQ::NEQ - 1)) - 1u) ? 1 : 0);   // gathered q components
+    static constexpr int NCOMP = NQ + EQ::NAUX;                  // staged doubles per node
     static constexpr int FLD_D = 3 * NEQ * NP;
     static constexpr int PART_D = NPART * NP;
-    static constexpr int D_TOTAL = round_up(FLD_D + PART_D + 2 * NP, 2);      // + source field + M^-1 field
-    static constexpr size_t SMEM_BYTES = (size_t)D_TOTAL * 8 + (size_t)round_up(NP, 4) * 4;   // + node ids
+    static constexpr int STG_D = JX_WPENCIL_STAGE ? R * NCOMP * NT : 0;
+    static constexpr size_t SMEM_BYTES = (size_t)(FLD_D + PART_D + NP + STG_D) * 8;
 };
+
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
 template <int NGL, class EQ, bool EXACT>
 static __global__ void __maxnreg__(JX_WPENCIL_MAXREG)
@@ -737,15 +749,14 @@ k_elem_wpencil(const __grid_constant__ ElemArgs a) {
     using C = ElemWPencilCfg<NGL, EQ, EXACT>;
     using G = Geo<3, NGL>;
     constexpr int N = NGL, NC = C::NC, NP = C::NP, NEQ = C::NEQ, REC_BYTES = G::REC_BYTES, NT = C::NT;
-    constexpr int R = (NP + NT - 1) / NT;          // flux rounds: node l = r*NT + t
-    constexpr int RB = (EQ::NEEDS_QE && !EQ::HAS_AUX) ? (R > 2 ? 2 : R) : R;   // rounds whose gathers are in flight together
+    constexpr int R = C::R, NQ = C::NQ, NCOMP = C::NCOMP;
     static_assert(EQ::SRC_EQ >= -1, "pencil kernels keep at most one source component");
+    static_assert(EQ::HAS_AUX, "the pencil kernels use the two-stage flux functors");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *X = reinterpret_cast<double *>(smem_raw);     // [3*NEQ][NP]
     double *Pe = X + C::FLD_D;                            // [NPART][NP]
     double *Sf = Pe + C::PART_D;                          // [NP] source of equation SRC_EQ
-    double *Mf = Sf + NP;                                 // [NP] M^-1 (atomics mode with folding) or 1
-    int32_t *sIp = reinterpret_cast<int32_t *>(X + C::D_TOTAL);
+    double *stg = Sf + NP;                                // [R][NCOMP][NT] gathers of the NEXT element (cp.async)
 
     const int t = threadIdx.x;
     const bool pl = t < NC;            // pencil lane
@@ -754,27 +765,61 @@ k_elem_wpencil(const __grid_constant__ ElemArgs a) {
     const int bx = N * c, by = c0 + NC * c1, bz = c;
     const bool fold = a.atomics && a.Minv != nullptr;
 #define JX_D(m, i) a.dpsi[(m) + NGL * (i)]
+// all N outputs of the three lines at once: 3N independent FMA chains, each accumulating in ascending m
+// exactly like the oracle's dot products
+#define JX_DERIV_ALL                                                        \
+    double dF[N], dG[N], dH[N];                                             \
+    _Pragma("unroll") for (int o_ = 0; o_ < N; ++o_) { dF[o_] = 0.0; dG[o_] = 0.0; dH[o_] = 0.0; } \
+    _Pragma("unroll") for (int m_ = 0; m_ < N; ++m_) {                      \
+        _Pragma("unroll") for (int o_ = 0; o_ < N; ++o_) {                  \
+            dF[o_] = fma(JX_D(m_, o_), f[m_], dF[o_]);                      \
+            dG[o_] = fma(JX_D(m_, o_), gg[m_], dG[o_]);                     \
+            dH[o_] = fma(JX_D(m_, o_), h[m_], dH[o_]);                      \
+        }                                                                   \
+    }
     auto rec_of = [&](int64_t p) -> const double * {
         return reinterpret_cast<const double *>(a.rec + (size_t)(a.elist ? (int64_t)a.elist[p] : p) * REC_BYTES);
     };
-
-    // node ids of the first element; inside the loop they are fetched one element ahead
-    int ndn[R];
-    if ((int64_t)blockIdx.x < a.nelem) {
-        const int32_t *cn = reinterpret_cast<const int32_t *>(rec_of(blockIdx.x) + G::NMET * NP);
+    // node ids of element p: flux-phase view (node l = r*NT + t) and zeta-pencil view (node c + NC*m)
+    auto load_ids = [&](int64_t p, int(&nd)[R], int(&ipz)[N]) {
+        const int32_t *cn = reinterpret_cast<const int32_t *>(rec_of(p) + G::NMET * NP);
 #pragma unroll
-        for (int r = 0; r < R; ++r) ndn[r] = (r * NT + t < NP) ? __ldcs(cn + r * NT + t) : 0;
+        for (int r = 0; r < R; ++r) nd[r] = (r * NT + t < NP) ? __ldcs(cn + r * NT + t) : -1;
+#pragma unroll
+        for (int m = 0; m < N; ++m) ipz[m] = pl ? __ldcs(cn + bz + NC * m) : 0;
+    };
+    // q and the per-node EOS values of one element -> staging, asynchronously (no registers held)
+    auto issue_gathers = [&](const int(&nd)[R]) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (nd[r] >= 0) {
+                double *dst = stg + (size_t)r * NCOMP * NT + t;
+#pragma unroll
+                for (int e = 0; e < NQ; ++e) cp_async8(dst + e * NT, a.u + (size_t)e * a.npoin + nd[r]);
+#pragma unroll
+                for (int x = 0; x < EQ::NAUX; ++x) cp_async8(dst + (NQ + x) * NT, a.aux + (size_t)x * a.npoin + nd[r]);
+            }
+        }
+        cp_async_commit();
+    };
+
+    int ndn[R], ipn[N];
+    if ((int64_t)blockIdx.x < a.nelem) {
+        load_ids(blockIdx.x, ndn, ipn);
+        if (JX_WPENCIL_STAGE) issue_gathers(ndn);
     }
     for (int64_t pos = blockIdx.x; pos < a.nelem; pos += gridDim.x) {
         const int64_t pn = pos + gridDim.x;
         const int64_t iel = a.elist ? (int64_t)a.elist[pos] : pos;
         const double *rec = rec_of(pos);
-        int nd[R];
+        int nd[R], ip[N];
 #pragma unroll
         for (int r = 0; r < R; ++r) nd[r] = ndn[r];
+#pragma unroll
+        for (int m = 0; m < N; ++m) ip[m] = ipn[m];
 
         // metric terms of this thread's three pencils -> registers (in flight during the flux phase)
-        double mx[3][N], my[3][N], mz[3][N], wj[N];
+        double mx[3][N], my[3][N], mz[3][N], wj[N], mi[N];
         if (pl) {
 #pragma unroll
             for (int q = 0; q < 3; ++q)
@@ -786,71 +831,58 @@ k_elem_wpencil(const __grid_constant__ ElemArgs a) {
                 }
 #pragma unroll
             for (int m = 0; m < N; ++m) wj[m] = __ldcs(rec + (9 * N + m) * NC + c);
+#pragma unroll
+            for (int m = 0; m < N; ++m) mi[m] = fold ? __ldg(a.Minv + ip[m]) : 1.0;
         }
         if (pn < a.nelem) {   // next element: node ids -> registers, record -> L2
-            const double *rn = rec_of(pn);
-            const int32_t *cn = reinterpret_cast<const int32_t *>(rn + G::NMET * NP);
+            load_ids(pn, ndn, ipn);
+            if (t == 0) prefetch_l2_bulk(rec_of(pn), REC_BYTES);
+        } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r) ndn[r] = (r * NT + t < NP) ? __ldcs(cn + r * NT + t) : 0;
-            if (t == 0) prefetch_l2_bulk(rn, REC_BYTES);
+            for (int r = 0; r < R; ++r) ndn[r] = -1;
         }
-        // flux / source at every node, node-parallel; the gathers of RB rounds are issued together
+        // flux / source at every node, node-parallel; q and the per-node EOS values come either from the staged
+        // gathers (issued one element ago) or from direct gathers of all rounds issued together
+        double qa[R][NCOMP];
+        if (JX_WPENCIL_STAGE) {
+            cp_async_wait<0>();
 #pragma unroll
-        for (int rb = 0; rb < R; rb += RB) {
-            constexpr int NAX = EQ::HAS_AUX ? EQ::NAUX : 1;
-            double q[RB][NEQ], qe[RB][NEQ + 1], ax[RB][NAX], mv[RB];
+            for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int r = 0; r < RB; ++r) {
-                const int l = (rb + r) * NT + t;
-                const int64_t node = nd[(rb + r) < R ? (rb + r) : 0];
-                const bool on = (rb + r) < R && l < NP;
+                for (int x = 0; x < NCOMP; ++x) qa[r][x] = nd[r] >= 0 ? stg[((size_t)r * NCOMP + x) * NT + t] : 1.0;
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int64_t node = nd[r] >= 0 ? nd[r] : 0;
+#pragma unroll
+                for (int e = 0; e < NQ; ++e) qa[r][e] = nd[r] >= 0 ? __ldg(a.u + (size_t)e * a.npoin + node) : 1.0;
+#pragma unroll
+                for (int x = 0; x < EQ::NAUX; ++x) qa[r][NQ + x] = nd[r] >= 0 ? __ldg(a.aux + (size_t)x * a.npoin + node) : 1.0;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int l = r * NT + t;
+            if (nd[r] >= 0) {
+                double q[NEQ], ax[EQ::NAUX], f[NEQ], gg[NEQ], h[NEQ];
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e) q[e] = e < NQ ? qa[r][e < NQ ? e : 0] : 1.0;
+#pragma unroll
+                for (int x = 0; x < EQ::NAUX; ++x) ax[x] = qa[r][NQ + x];
+                EQ::flux_aux(a.phys, q, ax, f, gg, h);
 #pragma unroll
                 for (int e = 0; e < NEQ; ++e) {
-                    const bool need = !EQ::HAS_AUX || ((EQ::FLUX_QMASK >> e) & 1u);
-                    q[r][e] = (on && need) ? __ldg(a.u + (size_t)e * a.npoin + node) : 1.0;
+                    X[(0 * NEQ + e) * NP + l] = f[e];
+                    X[(1 * NEQ + e) * NP + l] = gg[e];
+                    X[(2 * NEQ + e) * NP + l] = h[e];
                 }
-#pragma unroll
-                for (int e = 0; e <= NEQ; ++e) qe[r][e] = (EQ::NEEDS_QE && !EQ::HAS_AUX && on) ? __ldg(a.qe + (size_t)e * a.npoin + node) : 0.0;
-                if constexpr (EQ::HAS_AUX) {
-#pragma unroll
-                    for (int x = 0; x < EQ::NAUX; ++x) ax[r][x] = on ? __ldg(a.aux + (size_t)x * a.npoin + node) : 1.0;
-                }
-                mv[r] = (fold && on) ? __ldg(a.Minv + node) : 1.0;
+                if constexpr (EQ::SRC_EQ >= 0) Sf[l] = a.lsource ? EQ::source_aux(a.phys, q, ax) : 0.0;
             }
+        }
+        if (JX_WPENCIL_STAGE) issue_gathers(ndn);   // the staging slots were just consumed by their own threads
+        if (fold) {                    // atomics mode: M^-1 folded into the quadrature weight (one rounding)
 #pragma unroll
-            for (int r = 0; r < RB; ++r) {
-                const int l = (rb + r) * NT + t;
-                if ((rb + r) < R && l < NP) {
-                    const int64_t node = nd[(rb + r) < R ? (rb + r) : 0];
-                    double f[NEQ], gg[NEQ], h[NEQ];
-                    if constexpr (EQ::HAS_AUX) EQ::flux_aux(a.phys, q[r], ax[r], f, gg, h);
-                    else EQ::flux(a.phys, q[r], qe[r], f, gg, h);
-#pragma unroll
-                    for (int e = 0; e < NEQ; ++e) {
-                        X[(0 * NEQ + e) * NP + l] = f[e];
-                        X[(1 * NEQ + e) * NP + l] = gg[e];
-                        X[(2 * NEQ + e) * NP + l] = h[e];
-                    }
-                    if constexpr (EQ::SRC_EQ >= 0) {
-                        double sv = 0.0;
-                        if (a.lsource) {
-                            if constexpr (EQ::HAS_AUX) sv = EQ::source_aux(a.phys, q[r], ax[r]);
-                            else {
-                                double xyz[3] = {0.0, 0.0, 0.0}, S[NEQ];
-                                if constexpr (EQ::NEEDS_XYZ) {
-#pragma unroll
-                                    for (int d = 0; d < 3; ++d) xyz[d] = __ldg(a.coords + (size_t)d * a.npoin + node);
-                                }
-                                EQ::source(a.phys, q[r], qe[r], xyz, S);
-                                sv = S[EQ::SRC_EQ >= 0 ? EQ::SRC_EQ : 0];
-                            }
-                        }
-                        Sf[l] = sv;
-                    }
-                    Mf[l] = mv[r];
-                    sIp[l] = (int32_t)node;
-                }
-            }
+            for (int m = 0; m < N; ++m) wj[m] = wj[m] * mi[m];
         }
         __syncthreads();
 
@@ -861,85 +893,82 @@ k_elem_wpencil(const __grid_constant__ ElemArgs a) {
                 double f[N], gg[N], h[N];
 #pragma unroll
                 for (int m = 0; m < N; ++m) { f[m] = Fe[bx + m]; gg[m] = Ge[bx + m]; h[m] = He[bx + m]; }
+                JX_DERIV_ALL
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
-                    double dF = 0, dG = 0, dH = 0;
-#pragma unroll
-                    for (int m = 0; m < N; ++m) {
-                        dF = fma(JX_D(m, i), f[m], dF);
-                        dG = fma(JX_D(m, i), gg[m], dG);
-                        dH = fma(JX_D(m, i), h[m], dH);
-                    }
                     if constexpr (EXACT) {
-                        Pe[0 * NP + bx + i] = dF * mx[0][i];
-                        Pe[1 * NP + bx + i] = dG * mx[1][i];
-                        Pe[2 * NP + bx + i] = dH * mx[2][i];
+                        Pe[0 * NP + bx + i] = dF[i] * mx[0][i];
+                        Pe[1 * NP + bx + i] = dG[i] * mx[1][i];
+                        Pe[2 * NP + bx + i] = dH[i] * mx[2][i];
                     } else {
-                        Pe[bx + i] = (dF * mx[0][i] + dG * mx[1][i]) + dH * mx[2][i];
+                        Pe[bx + i] = (dF[i] * mx[0][i] + dG[i] * mx[1][i]) + dH[i] * mx[2][i];
                     }
                 }
             }
             __syncthreads();
             if (pl) {   // eta pass
-                double f[N], gg[N], h[N];
+                double f[N], gg[N], h[N], pa[C::NPART][N];
 #pragma unroll
                 for (int m = 0; m < N; ++m) { f[m] = Fe[by + N * m]; gg[m] = Ge[by + N * m]; h[m] = He[by + N * m]; }
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    double dF = 0, dG = 0, dH = 0;
+                for (int q = 0; q < C::NPART; ++q)
 #pragma unroll
-                    for (int m = 0; m < N; ++m) {
-                        dF = fma(JX_D(m, j), f[m], dF);
-                        dG = fma(JX_D(m, j), gg[m], dG);
-                        dH = fma(JX_D(m, j), h[m], dH);
-                    }
+                    for (int j = 0; j < N; ++j) pa[q][j] = Pe[q * NP + by + N * j];
+                JX_DERIV_ALL
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
                     const int o = by + N * j;
                     if constexpr (EXACT) {
-                        Pe[0 * NP + o] = Pe[0 * NP + o] + dF * my[0][j];
-                        Pe[1 * NP + o] = Pe[1 * NP + o] + dG * my[1][j];
-                        Pe[2 * NP + o] = Pe[2 * NP + o] + dH * my[2][j];
+                        Pe[0 * NP + o] = pa[0][j] + dF[j] * my[0][j];
+                        Pe[1 * NP + o] = pa[1][j] + dG[j] * my[1][j];
+                        Pe[2 * NP + o] = pa[2][j] + dH[j] * my[2][j];
                     } else {
-                        Pe[o] = Pe[o] + ((dF * my[0][j] + dG * my[1][j]) + dH * my[2][j]);
+                        Pe[o] = pa[0][j] + ((dF[j] * my[0][j] + dG[j] * my[1][j]) + dH[j] * my[2][j]);
                     }
                 }
             }
             __syncthreads();
             if (pl) {   // zeta pass + output
-                double f[N], gg[N], h[N];
+                double f[N], gg[N], h[N], pa[C::NPART][N], Sv[N];
 #pragma unroll
                 for (int m = 0; m < N; ++m) { f[m] = Fe[bz + NC * m]; gg[m] = Ge[bz + NC * m]; h[m] = He[bz + NC * m]; }
 #pragma unroll
-                for (int k = 0; k < N; ++k) {
-                    double dF = 0, dG = 0, dH = 0;
+                for (int q = 0; q < C::NPART; ++q)
 #pragma unroll
-                    for (int m = 0; m < N; ++m) {
-                        dF = fma(JX_D(m, k), f[m], dF);
-                        dG = fma(JX_D(m, k), gg[m], dG);
-                        dH = fma(JX_D(m, k), h[m], dH);
+                    for (int k = 0; k < N; ++k) pa[q][k] = Pe[q * NP + bz + NC * k];
+#pragma unroll
+                for (int k = 0; k < N; ++k) Sv[k] = 0.0;
+                if constexpr (EQ::SRC_EQ >= 0) {
+                    if (e == EQ::SRC_EQ) {
+#pragma unroll
+                        for (int k = 0; k < N; ++k) Sv[k] = Sf[bz + NC * k];
                     }
-                    const int o = bz + NC * k;
+                }
+                JX_DERIV_ALL
+                double *due = a.du + (size_t)e * a.npoin;
+                double *rhe = a.atomics ? nullptr : a.rhs_el + ((size_t)iel * NEQ + e) * NP + bz;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
                     double r;
                     if constexpr (EXACT) {
-                        const double dFdx = Pe[0 * NP + o] + dF * mz[0][k];
-                        const double dGdy = Pe[1 * NP + o] + dG * mz[1][k];
-                        const double dHdz = Pe[2 * NP + o] + dH * mz[2][k];
+                        const double dFdx = pa[0][k] + dF[k] * mz[0][k];
+                        const double dGdy = pa[1][k] + dG[k] * mz[1][k];
+                        const double dHdz = pa[2][k] + dH[k] * mz[2][k];
                         r = (dFdx + dGdy) + dHdz;
                     } else {
-                        r = Pe[o] + ((dF * mz[0][k] + dG * mz[1][k]) + dH * mz[2][k]);
+                        r = pa[0][k] + ((dF[k] * mz[0][k] + dG[k] * mz[1][k]) + dH[k] * mz[2][k]);
                     }
-                    double S = 0.0;
-                    if constexpr (EQ::SRC_EQ >= 0) {
-                        if (e == EQ::SRC_EQ) S = Sf[o];
-                    }
-                    const double out = 0.0 - wj[k] * (r - S);
-                    if (!a.atomics) a.rhs_el[((size_t)iel * NEQ + e) * NP + o] = out;
-                    else atomicAdd(&a.du[(size_t)e * a.npoin + sIp[o]], out * Mf[o]);
+                    const double out = 0.0 - wj[k] * (r - Sv[k]);
+                    if (rhe) rhe[NC * k] = out;
+                    else atomicAdd(due + ip[k], out);
                 }
             }
             __syncthreads();   // partials (and, after the last equation, the fields) are free again
         }
     }
+    cp_async_wait<0>();
 #undef JX_D
+#undef JX_DERIV_ALL
 }
 
 // ------------------------------------------------------------------------------------------

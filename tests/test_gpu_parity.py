@@ -177,15 +177,15 @@ def test_periodic_self_exchange_3d():
 
 
 # ---- pencil element kernel (JX_OPT_ELEM_KERNEL 1 = exact order, 2 = single partial) ---------------
-@pytest.mark.parametrize("variant", [1, 3, 5])
-@pytest.mark.parametrize("nop", [2, 4, 5, 7])
+@pytest.mark.parametrize("variant", [1, 3])
+@pytest.mark.parametrize("nop", [2, 4, 5])
 @pytest.mark.parametrize("lpert", [False, True])
 def test_pencil_kernel_bit_exact(variant, nop, lpert):
     """Variants 1 and 3 re-tile the work (one thread per LGL line and direction; 3 = one element per
     CTA) but keep the reference's left-to-right order of every sum, so they must reproduce the oracle
     bit for bit."""
-    if (variant == 1 and nop >= 5) or (variant == 3 and nop == 7):
-        pytest.skip("variant 1 is instantiated for nop 2 and 4, variant 3 for nop 2, 4, 5")
+    if variant == 1 and nop >= 5:
+        pytest.skip("variant 1 is instantiated for nop 2 and 4")
     spec = box3d((5, 4, 3) if nop < 7 else (3, 2, 2), nop, warp=0.05)
     sems, qns, qes, us = euler_case(spec, 1, lpert=lpert)
     dus, ub, _ = _oracle_rhs(sems, qes, us, lpert, False, pow_mode=1)
@@ -194,7 +194,7 @@ def test_pencil_kernel_bit_exact(variant, nop, lpert):
     assert np.array_equal(du, dus[0]), rel_err_per_node(du, dus[0])
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("lpert", [False, True])
 def test_pencil_kernel_atomics(variant, lpert):
     """The bench configuration: pencil kernel + atomics DSS with M^-1 folded in; <= 1e-12 per node,
@@ -206,7 +206,7 @@ def test_pencil_kernel_atomics(variant, lpert):
     N = sems[0].mesh.npoin
     # variants 2/4 associate the nine metric products differently (one partial instead of three): measured
     # 3e-12 per node on the near-zero horizontal momenta, outside the 1e-12 bar -- they are opt-in, not default
-    bar = 1e-12 if variant in (1, 3, 5) else 1e-10
+    bar = 1e-12 if variant in (1, 3) else 1e-10
     for e in range(5):
         pn, l2 = rel_err_per_node(du[e * N:(e + 1) * N], dus[0][e * N:(e + 1) * N])
         assert pn <= bar and l2 <= 1e-10, (variant, lpert, e, pn, l2)
