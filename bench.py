@@ -195,9 +195,9 @@ def main():
     ap.add_argument("--nop", type=int, default=4)
     ap.add_argument("--visc", action="store_true")
     ap.add_argument("--pert", action="store_true")
-    ap.add_argument("--dss-mode", type=int, default=int(os.environ.get("JX_DSS_MODE", "0")))
+    ap.add_argument("--dss-mode", type=int, default=int(os.environ.get("JX_DSS_MODE", "1")))
     ap.add_argument("--pow-mode", type=int, default=int(os.environ.get("JX_POW_MODE", "1")))
-    ap.add_argument("--elem-kernel", type=int, default=int(os.environ.get("JX_ELEM_KERNEL", "0")))
+    ap.add_argument("--elem-kernel", type=int, default=int(os.environ.get("JX_ELEM_KERNEL", "3")))
     ap.add_argument("--ref-nel", type=int, default=12)
     ap.add_argument("--cpu-nel", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
