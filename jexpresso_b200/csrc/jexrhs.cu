@@ -352,10 +352,13 @@ extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *c
     const int np = c->np, q = c->neqs;
     const int64_t total = E * np;
     const size_t nq = (size_t)N * q;
+    const bool grouped = c->ks->rec_layout == 4;      // group records (k_elem_gpencil)
+    const int64_t ngroups = grouped ? (E + c->ks->elems_per_block - 1) / c->ks->elems_per_block : 0;
+    const size_t rec_total = grouped ? (size_t)ngroups * c->ks->group_bytes : (size_t)E * c->rec_bytes;
     int rc;
     if ((rc = dalloc(c, &c->u, nq)) || (rc = dalloc(c, &c->du, nq)) || (rc = dalloc(c, &c->tmp, nq)) ||
         (rc = dalloc(c, &c->Minv, (size_t)N)) || (rc = dalloc(c, &c->qe, (size_t)N * (q + 1))) ||
-        (rc = dalloc(c, &c->coords, (size_t)N * c->nsd)) || (rc = dalloc(c, &c->rec, (size_t)E * c->rec_bytes)) ||
+        (rc = dalloc(c, &c->coords, (size_t)N * c->nsd)) || (rc = dalloc(c, &c->rec, rec_total)) ||
         (rc = dalloc(c, &c->n2e_ptr, (size_t)N + 1)) || (rc = dalloc(c, &c->n2e_idx, (size_t)total)))
         return rc;
     CK(cudaMemsetAsync(c->u, 0, nq * 8, c->stream));
@@ -388,8 +391,29 @@ extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *c
     ra.omega = d_omega; ra.connijk = d_conn; ra.rec = c->rec; ra.nelem = E; ra.nsd = c->nsd; ra.ngl = c->ngl; ra.np = np;
     ra.nmet = c->nmet; ra.npp = (np + 3) / 4 * 4; ra.rec_bytes = c->rec_bytes; ra.src = nullptr;
     ra.layout = c->ks->rec_layout;
-    if (total > 0) {
-        CKC(cudaMemsetAsync(c->rec, 0, (size_t)E * c->rec_bytes, c->stream));
+    if (total > 0 && grouped) {
+        const KernelSet *ks = c->ks;
+        GroupRetileArgs ga;
+        ga.src = nullptr; ga.omega = d_omega; ga.Minv = c->Minv; ga.connijk = d_conn; ga.rec = c->rec; ga.nelem = E;
+        ga.ngl = c->ngl; ga.epb = ks->elems_per_block; ga.nt = ks->group_nt; ga.group_bytes = ks->group_bytes;
+        ga.zid_off = ks->zid_off; ga.fid_off = ks->fid_off;
+        for (int ps = 0; ps < 3; ++ps)
+            for (int d = 0; d < 3; ++d) ga.mult[ps][d] = ks->group_mult[ps][d];
+        CKC(cudaMemsetAsync(c->rec, 0, rec_total, c->stream));
+        ga.slot = -1;
+        k_retile_group<<<nblk(total, 256), 256, 0, c->stream>>>(ga);
+        for (int m = 0; m < c->nmet; ++m) {
+            if (!metrics[m]) { cleanup(); return fail(c, JX_EINVAL, "metric array %d is null", m); }
+            CKC(cudaMemcpyAsync(d_stage, metrics[m], (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
+            ga.src = d_stage; ga.slot = m;
+            k_retile_group<<<nblk(total, 256), 256, 0, c->stream>>>(ga);
+            CKC(cudaStreamSynchronize(c->stream));
+        }
+        ga.slot = -2;                                  // -(omega*J*Minv): needs the ids, omega*J and Minv in place
+        k_retile_group<<<nblk(total, 256), 256, 0, c->stream>>>(ga);
+        c->launches += c->nmet + 2;
+    } else if (total > 0) {
+        CKC(cudaMemsetAsync(c->rec, 0, rec_total, c->stream));
         ra.slot = -1;
         k_retile<<<nblk(total, 256), 256, 0, c->stream>>>(ra);
         for (int m = 0; m < c->nmet; ++m) {

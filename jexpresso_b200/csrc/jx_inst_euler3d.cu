@@ -21,8 +21,14 @@ namespace jx {
     JX_WSET(NGL, true, true, true), JX_WSET(NGL, false, false, false), JX_WSET(NGL, false, true, false), \
     JX_WSET(NGL, true, false, false), JX_WSET(NGL, true, true, false)
 
+#define JX_GSET(NGL, EPB, VAR, PERT, POW) make_gpencil_set<NGL, EulerTheta<3, PERT, POW>, EPB>(JX_EQ_EULER_THETA, PERT, POW, VAR)
+#define JX_GROW(NGL, EPB, VAR) \
+    JX_GSET(NGL, EPB, VAR, false, false), JX_GSET(NGL, EPB, VAR, false, true), JX_GSET(NGL, EPB, VAR, true, false), \
+    JX_GSET(NGL, EPB, VAR, true, true)
+
 const KernelSet *lookup_euler_theta_3d(int ngl, int lpert, int jxpow, int lvisc, int variant) {
-    static const KernelSet table[] = {JX_ROW(3), JX_ROW(5), JX_ROW(6), JX_ROW(8), JX_PROW(3), JX_PROW(5), JX_WROW(3), JX_WROW(5), JX_WROW(6)};
+    static const KernelSet table[] = {JX_ROW(3), JX_ROW(5), JX_ROW(6), JX_ROW(8), JX_PROW(3), JX_PROW(5), JX_WROW(3), JX_WROW(5), JX_WROW(6),
+                                      JX_GROW(3, 7, 5), JX_GROW(5, 5, 5), JX_GROW(5, 1, 6)};
     for (const KernelSet &k : table)
         if (k.ngl == ngl && k.lpert == lpert && k.jxpow == jxpow && k.lvisc == lvisc && k.variant == variant) return &k;
     return nullptr;

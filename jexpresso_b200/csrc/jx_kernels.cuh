@@ -972,6 +972,304 @@ k_elem_wpencil(const __grid_constant__ ElemArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused per-element kernel, variant "gpencil" (3D, inviscid, exact order): pencils of a GROUP of EPB
+// elements flattened over the CTA's lanes.  profiles/r01e showed the one-element-per-warp kernel bound by
+// the LSU data pipe (86 % busy) with 25 of 32 lanes active at nop=4 and a 2-way bank conflict in its eta
+// pass.  Here
+//   * EPB*n^2 pencils fill the warps (nop=4: 5 elements = 125 pencils on 128 lanes, 97.6 %);
+//   * every pass decodes the lane id into (element slot, c0, c1) with its OWN digit order, chosen by
+//     scripts/analysis/bank_search2.py so that all three passes are bank-conflict free without padding
+//     (GPLayout);
+//   * the xi and eta passes write their metric-weighted derivatives into separate tiles (A1, A2) and the
+//     zeta pass adds (A1 + A2) + a3 -- the reference's left-to-right order (rhs.jl:1679-1696) with one block
+//     barrier less per equation and no read-modify-write of a partial;
+//   * the group record holds the metric terms as lane-major streams per pass (one coalesced LDG per stream),
+//     the node ids in the zeta-pass and flux-phase views, the quadrature weight omega*J and its pre-folded,
+//     negated product with M^-1 (atomics mode: no M^-1 gather, no "0 -" per output); the flux phase walks the
+//     group's nodes with (i, element slot) fastest, so the q gathers and the zeta-pass RED.ADDs of x-adjacent
+//     elements fall into the same 128-byte lines.
+// Arithmetic per output is the same IEEE sequence as k_elem_node / the oracle (deterministic mode:
+// bit-identical; atomics mode: identical up to the sign of zero and the order of the DSS sum).
+// ------------------------------------------------------------------------------------------
+struct DigitOrder { int d0, d1, d2; };     // digits fastest -> slowest; 0 = element slot s, 1 = c0, 2 = c1
+template <int NGL, int EPB>
+struct GPLayout {                           // generic: unpadded, element-major lanes in every pass
+    static constexpr int PJ = NGL, PK = NGL * NGL, ES = NGL * NGL * NGL;
+    static constexpr DigitOrder XI{1, 2, 0}, ETA{1, 2, 0}, ZETA{1, 2, 0};
+};
+template <>
+struct GPLayout<5, 5> {                     // conflict free in all three passes (bank_search2.py 5 5)
+    static constexpr int PJ = 5, PK = 25, ES = 125;
+    static constexpr DigitOrder XI{1, 2, 0}, ETA{2, 0, 1}, ZETA{0, 1, 2};
+};
+__host__ __device__ constexpr int gp_radix(int digit, int n, int epb) { return digit == 0 ? epb : n; }
+// multiplier of digit `which` in lane id p = s*M0 + c0*M1 + c1*M2
+__host__ __device__ constexpr int gp_mult(DigitOrder o, int which, int n, int epb) {
+    return o.d0 == which ? 1 : (o.d1 == which ? gp_radix(o.d0, n, epb) : gp_radix(o.d0, n, epb) * gp_radix(o.d1, n, epb));
+}
+__host__ __device__ constexpr int gp_digit(DigitOrder o, int which, int p, int n, int epb) {
+    return o.d0 == which ? p % gp_radix(o.d0, n, epb)
+                         : (o.d1 == which ? (p / gp_radix(o.d0, n, epb)) % gp_radix(o.d1, n, epb)
+                                          : p / (gp_radix(o.d0, n, epb) * gp_radix(o.d1, n, epb)));
+}
+
+template <int NGL, class EQ, int EPB>
+struct ElemGPencilCfg {
+    using L = GPLayout<NGL, EPB>;
+    static constexpr int N = NGL, NC = NGL * NGL, NP = NGL * NGL * NGL, NEQ = EQ::NEQ;
+    static constexpr int NPEN = EPB * NC;                       // pencils per group and direction
+    static constexpr int NT = round_up(NPEN, 32);
+    static constexpr int NNODE = EPB * NP;
+    static constexpr int R = (NNODE + NT - 1) / NT;             // flux rounds: group node n = r*NT + t
+    static constexpr int GB = round_up(EPB * L::ES, 2);         // doubles per field tile of a group
+    static constexpr bool PLAIN = (L::PJ == NGL && L::PK == NGL * NGL && L::ES == NGL * NGL * NGL);
+    static constexpr int NFLD = 3 * NEQ;
+    static constexpr int NTILE = NFLD + 6 + (EQ::SRC_EQ >= 0 ? 1 : 0);
+    static constexpr size_t SMEM_BYTES = (size_t)NTILE * GB * 8;
+    static constexpr int NQ = EQ::NEQ - (EQ::FLUX_QMASK == ((1u << (EQ::NEQ - 1)) - 1u) ? 1 : 0);
+    static constexpr int NCOMP = NQ + EQ::NAUX;
+    // group record: 11n lane-major double streams, then int32 zeta-view ids [n][NT], then flux-view ids [R*NT]
+    static constexpr int NSTREAM = 11 * NGL;
+    static constexpr int ZID_OFF = NSTREAM * NT * 8;
+    static constexpr int FID_OFF = ZID_OFF + NGL * NT * 4;
+    static constexpr int GROUP_BYTES = round_up(FID_OFF + R * NT * 4, 128);
+    static constexpr int MINB = (SMEM_BYTES + 1024) * 2 <= 233472 ? 2 : 1;
+};
+
+struct GroupRetileArgs {
+    const double *src;        // one metric array [E, n, n, n], element fastest (device copy); slot >= 0
+    const double *omega;
+    const double *Minv;       // slot -2
+    const int64_t *connijk;   // slot -1
+    char *rec;
+    int64_t nelem;
+    int ngl, epb, nt, group_bytes, zid_off, fid_off;
+    int mult[3][3];           // [pass xi/eta/zeta][digit s/c0/c1]
+    int slot;                 // 0..8 metric term, 9 = Je (stored as omega*J), -1 = node ids, -2 = -(omega*J*Minv)
+};
+
+// element-fastest Julia arrays -> group records; thread = (element, local node), element fastest
+static __global__ void k_retile_group(GroupRetileArgs a) {
+    const int n = a.ngl, np = n * n * n;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= a.nelem * np) return;
+    const int64_t iel = tid % a.nelem;
+    const int l = (int)(tid / a.nelem);
+    const int i = l % n, j = (l / n) % n, k = l / (n * n);
+    const int64_t g = iel / a.epb;
+    const int s = (int)(iel % a.epb);
+    char *rec = a.rec + (size_t)g * a.group_bytes;
+    double *met = reinterpret_cast<double *>(rec);
+    int32_t *zid = reinterpret_cast<int32_t *>(rec + a.zid_off);
+    int32_t *fid = reinterpret_cast<int32_t *>(rec + a.fid_off);
+    const int pxi = s * a.mult[0][0] + j * a.mult[0][1] + k * a.mult[0][2];    // xi-pencil (j,k), node i
+    const int pet = s * a.mult[1][0] + i * a.mult[1][1] + k * a.mult[1][2];    // eta-pencil (i,k), node j
+    const int pze = s * a.mult[2][0] + i * a.mult[2][1] + j * a.mult[2][2];    // zeta-pencil (i,j), node k
+    const size_t src = (size_t)iel + (size_t)a.nelem * l;
+    if (a.slot == -1) {
+        const int32_t ip = (int32_t)(a.connijk[src] - 1);
+        zid[k * a.nt + pze] = ip;
+        fid[i + n * (s + a.epb * (j + n * k))] = ip;     // flux-phase order: (i, slot) fastest -> x-adjacent elements coalesce
+    } else if (a.slot == -2) {
+        const int32_t ip = zid[k * a.nt + pze];
+        const double wJ = met[(size_t)(9 * n + k) * a.nt + pze];
+        met[(size_t)(10 * n + k) * a.nt + pze] = -(wJ * a.Minv[ip]);
+    } else if (a.slot < 3) {
+        met[(size_t)(a.slot * n + i) * a.nt + pxi] = a.src[src];
+    } else if (a.slot < 6) {
+        met[(size_t)(3 * n + (a.slot - 3) * n + j) * a.nt + pet] = a.src[src];
+    } else if (a.slot < 9) {
+        met[(size_t)(6 * n + (a.slot - 6) * n + k) * a.nt + pze] = a.src[src];
+    } else {
+        const double wjk = a.omega[j] * a.omega[k];      // rhs.jl:1636-1643
+        met[(size_t)(9 * n + k) * a.nt + pze] = a.omega[i] * wjk * a.src[src];
+    }
+}
+
+template <int NGL, class EQ, int EPB>
+static __global__ void __launch_bounds__(ElemGPencilCfg<NGL, EQ, EPB>::NT, ElemGPencilCfg<NGL, EQ, EPB>::MINB)
+k_elem_gpencil(const __grid_constant__ ElemArgs a) {
+    using C = ElemGPencilCfg<NGL, EQ, EPB>;
+    using L = typename C::L;
+    constexpr int N = NGL, NC = C::NC, NP = C::NP, NEQ = C::NEQ, NT = C::NT, R = C::R, GB = C::GB;
+    constexpr int NQ = C::NQ, NCOMP = C::NCOMP;
+    constexpr int PJ = L::PJ, PK = L::PK, ES = L::ES;
+    static_assert(EQ::SRC_EQ >= -1, "pencil kernels keep at most one source component");
+    static_assert(EQ::HAS_AUX, "the pencil kernels use the two-stage flux functors");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *X = reinterpret_cast<double *>(smem_raw);     // [3*NEQ][GB] fluxes F, G, H of every equation
+    double *A = X + (size_t)C::NFLD * GB;                 // [6][GB]: A1 (xi) F,G,H then A2 (eta) F,G,H
+    double *Sf = A + 6 * GB;                              // [GB] source of equation SRC_EQ
+
+    const int t = threadIdx.x;
+    const bool pen = t < C::NPEN;
+    const int p = pen ? t : 0;
+    // per-pass lane decode: (element slot, c0, c1)
+    const int sx = gp_digit(L::XI, 0, p, N, EPB), jx_ = gp_digit(L::XI, 1, p, N, EPB), kx = gp_digit(L::XI, 2, p, N, EPB);
+    const int sy = gp_digit(L::ETA, 0, p, N, EPB), iy = gp_digit(L::ETA, 1, p, N, EPB), ky = gp_digit(L::ETA, 2, p, N, EPB);
+    const int sz = gp_digit(L::ZETA, 0, p, N, EPB), iz = gp_digit(L::ZETA, 1, p, N, EPB), jz = gp_digit(L::ZETA, 2, p, N, EPB);
+    const int bx = sx * ES + PJ * jx_ + PK * kx;       // xi-pencil:   node(m) = bx + m
+    const int by = sy * ES + iy + PK * ky;             // eta-pencil:  node(m) = by + PJ*m
+    const int bz = sz * ES + iz + PJ * jz;             // zeta-pencil: node(m) = bz + PK*m
+    const bool fold = a.atomics && a.Minv != nullptr;
+#define JX_D(m, i) a.dpsi[(m) + NGL * (i)]
+#define JX_DERIV_ALL                                                        \
+    double dF[N], dG[N], dH[N];                                             \
+    _Pragma("unroll") for (int o_ = 0; o_ < N; ++o_) { dF[o_] = 0.0; dG[o_] = 0.0; dH[o_] = 0.0; } \
+    _Pragma("unroll") for (int m_ = 0; m_ < N; ++m_) {                      \
+        _Pragma("unroll") for (int o_ = 0; o_ < N; ++o_) {                  \
+            dF[o_] = fma(JX_D(m_, o_), f[m_], dF[o_]);                      \
+            dG[o_] = fma(JX_D(m_, o_), gg[m_], dG[o_]);                     \
+            dH[o_] = fma(JX_D(m_, o_), h[m_], dH[o_]);                      \
+        }                                                                   \
+    }
+    const int64_t ngroups = (a.nelem + EPB - 1) / EPB;
+    auto fid_of = [&](int64_t g) { return reinterpret_cast<const int32_t *>(a.rec + (size_t)g * C::GROUP_BYTES + C::FID_OFF); };
+    int fidn[R];
+    if ((int64_t)blockIdx.x < ngroups) {
+        const int32_t *fi = fid_of(blockIdx.x);
+#pragma unroll
+        for (int r = 0; r < R; ++r) fidn[r] = __ldcs(fi + r * NT + t);
+    }
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int64_t gn = g + gridDim.x;
+        const int64_t e0 = g * EPB;
+        const int cnt = (int)(a.nelem - e0 < EPB ? a.nelem - e0 : EPB);
+        const char *rec = a.rec + (size_t)g * C::GROUP_BYTES;
+        const double *met = reinterpret_cast<const double *>(rec);
+        const int32_t *zid = reinterpret_cast<const int32_t *>(rec + C::ZID_OFF);
+
+        // gathers of q and the per-node EOS values, all rounds in flight together
+        double qa[R][NCOMP];
+        bool nv[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int n = r * NT + t;
+            nv[r] = n < C::NNODE && (n / N) % EPB < cnt;
+            const int64_t node = nv[r] ? fidn[r] : 0;
+#pragma unroll
+            for (int e = 0; e < NQ; ++e) qa[r][e] = nv[r] ? __ldg(a.u + (size_t)e * a.npoin + node) : 1.0;
+#pragma unroll
+            for (int x = 0; x < EQ::NAUX; ++x) qa[r][NQ + x] = nv[r] ? __ldg(a.aux + (size_t)x * a.npoin + node) : 1.0;
+        }
+        // metric terms of this lane's three pencils, quadrature weights and zeta-view node ids -> registers
+        // (the streams are lane-major and padded to NT columns: no predicate needed)
+        double mx[3][N], my[3][N], mz[3][N], wj[N];
+        int ip[N];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int m = 0; m < N; ++m) {
+                mx[q][m] = __ldcs(met + (q * N + m) * NT + t);
+                my[q][m] = __ldcs(met + (3 * N + q * N + m) * NT + t);
+                mz[q][m] = __ldcs(met + (6 * N + q * N + m) * NT + t);
+            }
+#pragma unroll
+        for (int m = 0; m < N; ++m) {
+            wj[m] = __ldcs(met + ((fold ? 10 : 9) * N + m) * NT + t);
+            ip[m] = __ldcs(zid + m * NT + t);
+        }
+        if (gn < ngroups) {   // next group: flux-view node ids -> registers, record -> L2
+            const int32_t *fi = fid_of(gn);
+#pragma unroll
+            for (int r = 0; r < R; ++r) fidn[r] = __ldcs(fi + r * NT + t);
+            constexpr int CH = 2048;
+            for (int off = t * CH; off < C::FID_OFF; off += NT * CH)
+                prefetch_l2_bulk(a.rec + (size_t)gn * C::GROUP_BYTES + off, (C::FID_OFF - off) < CH ? (C::FID_OFF - off) : CH);
+        }
+        // flux / source at every node of the group, node-parallel
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (nv[r]) {
+                const int n = r * NT + t;          // group node n = i + N*(slot + EPB*(j + N*k))
+                const int ad = ((n / N) % EPB) * ES + (n % N) + PJ * ((n / (N * EPB)) % N) + PK * (n / (NC * EPB));
+                double q[NEQ], ax[EQ::NAUX], f[NEQ], gg[NEQ], h[NEQ];
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e) q[e] = e < NQ ? qa[r][e < NQ ? e : 0] : 1.0;
+#pragma unroll
+                for (int x = 0; x < EQ::NAUX; ++x) ax[x] = qa[r][NQ + x];
+                EQ::flux_aux(a.phys, q, ax, f, gg, h);
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e) {
+                    X[(0 * NEQ + e) * GB + ad] = f[e];
+                    X[(1 * NEQ + e) * GB + ad] = gg[e];
+                    X[(2 * NEQ + e) * GB + ad] = h[e];
+                }
+                if constexpr (EQ::SRC_EQ >= 0) Sf[ad] = a.lsource ? EQ::source_aux(a.phys, q, ax) : 0.0;
+            }
+        }
+        __syncthreads();
+
+        const bool lx = pen && sx < cnt, ly = pen && sy < cnt, lz = pen && sz < cnt;
+#pragma unroll 1
+        for (int e = 0; e < NEQ; ++e) {
+            const double *Fe = X + (0 * NEQ + e) * GB, *Ge = X + (1 * NEQ + e) * GB, *He = X + (2 * NEQ + e) * GB;
+            if (lx) {   // xi pass: A1 = dF/dxi * xi_x, dG/dxi * xi_y, dH/dxi * xi_z
+                double f[N], gg[N], h[N];
+#pragma unroll
+                for (int m = 0; m < N; ++m) { f[m] = Fe[bx + m]; gg[m] = Ge[bx + m]; h[m] = He[bx + m]; }
+                JX_DERIV_ALL
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    A[0 * GB + bx + i] = dF[i] * mx[0][i];
+                    A[1 * GB + bx + i] = dG[i] * mx[1][i];
+                    A[2 * GB + bx + i] = dH[i] * mx[2][i];
+                }
+            }
+            if (ly) {   // eta pass: A2
+                double f[N], gg[N], h[N];
+#pragma unroll
+                for (int m = 0; m < N; ++m) { f[m] = Fe[by + PJ * m]; gg[m] = Ge[by + PJ * m]; h[m] = He[by + PJ * m]; }
+                JX_DERIV_ALL
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    A[3 * GB + by + PJ * j] = dF[j] * my[0][j];
+                    A[4 * GB + by + PJ * j] = dG[j] * my[1][j];
+                    A[5 * GB + by + PJ * j] = dH[j] * my[2][j];
+                }
+            }
+            __syncthreads();
+            if (lz) {   // zeta pass + output
+                double f[N], gg[N], h[N], a1[3][N], a2[3][N], Sv[N];
+#pragma unroll
+                for (int m = 0; m < N; ++m) { f[m] = Fe[bz + PK * m]; gg[m] = Ge[bz + PK * m]; h[m] = He[bz + PK * m]; }
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int k = 0; k < N; ++k) { a1[q][k] = A[q * GB + bz + PK * k]; a2[q][k] = A[(3 + q) * GB + bz + PK * k]; }
+#pragma unroll
+                for (int k = 0; k < N; ++k) Sv[k] = 0.0;
+                if constexpr (EQ::SRC_EQ >= 0) {
+                    if (e == EQ::SRC_EQ) {
+#pragma unroll
+                        for (int k = 0; k < N; ++k) Sv[k] = Sf[bz + PK * k];
+                    }
+                }
+                JX_DERIV_ALL
+                double *due = a.du + (size_t)e * a.npoin;
+                double *rhe = a.atomics ? nullptr : a.rhs_el + ((size_t)(e0 + sz) * NEQ + e) * NP + iz + N * jz;
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const double dFdx = (a1[0][k] + a2[0][k]) + dF[k] * mz[0][k];
+                    const double dGdy = (a1[1][k] + a2[1][k]) + dG[k] * mz[1][k];
+                    const double dHdz = (a1[2][k] + a2[2][k]) + dH[k] * mz[2][k];
+                    const double r = (dFdx + dGdy) + dHdz;
+                    if (fold) atomicAdd(due + ip[k], wj[k] * (r - Sv[k]));          // wj = -(omega*J*Minv)
+                    else {
+                        const double out = 0.0 - wj[k] * (r - Sv[k]);
+                        if (rhe) rhe[NC * k] = out;
+                        else atomicAdd(due + ip[k], out);
+                    }
+                }
+            }
+            __syncthreads();   // A tiles (and, after the last equation, the flux tiles) are free again
+        }
+    }
+#undef JX_D
+#undef JX_DERIV_ALL
+}
+
+// ------------------------------------------------------------------------------------------
 // self test of Recip::div against the compiler's correctly rounded `/` (jx_selftest(ctx, 0, n, &bad)).
 // Samples: b = density-like values in [1e-3, 1e3] and wide-range values, a = momentum-like values of
 // both signs, exact zeros, powers of two and near-overflow / near-underflow magnitudes.

@@ -141,4 +141,48 @@ KernelSet make_wpencil_set(int eq_id, int lpert, int jxpow) {
     return ks;
 }
 
+// variant 5 (group of elements per CTA, lanes full) / 6 (one element per CTA): group-pencil kernel, 3D inviscid,
+// exact order
+template <int NGL, class EQ, int EPB>
+struct GPencilKernel {
+    using C = ElemGPencilCfg<NGL, EQ, EPB>;
+    static cudaError_t prepare() {
+        return cudaFuncSetAttribute(k_elem_gpencil<NGL, EQ, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)C::SMEM_BYTES);
+    }
+    static int max_blocks() {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_gpencil<NGL, EQ, EPB>, C::NT, C::SMEM_BYTES);
+        return nb;
+    }
+    static void launch(const ElemArgs &a, int grid, cudaStream_t s) {
+        k_elem_gpencil<NGL, EQ, EPB><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+    }
+};
+
+template <int NGL, class EQ, int EPB>
+KernelSet make_gpencil_set(int eq_id, int lpert, int jxpow, int variant) {
+    using K = GPencilKernel<NGL, EQ, EPB>;
+    using C = typename K::C;
+    using L = typename C::L;
+    KernelSet ks;
+    ks.nsd = 3; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = 0; ks.variant = variant;
+    ks.neq = EQ::NEQ;
+    ks.elems_per_block = EPB;
+    ks.rec_layout = 4;
+    ks.nthreads = C::NT;
+    ks.smem_bytes = C::SMEM_BYTES;
+    ks.prepare = &K::prepare;
+    ks.max_blocks_per_sm = &K::max_blocks;
+    ks.launch_elem = &K::launch;
+    ks.launch_bc = &launch_bc_t<EQ>;
+    ks.launch_gather = &launch_gather_t<EQ::NEQ>;
+    ks.launch_aux = &launch_aux_t<EQ>;
+    ks.group_bytes = C::GROUP_BYTES; ks.group_nt = C::NT; ks.zid_off = C::ZID_OFF; ks.fid_off = C::FID_OFF;
+    const DigitOrder ord[3] = {L::XI, L::ETA, L::ZETA};
+    for (int ps = 0; ps < 3; ++ps)
+        for (int d = 0; d < 3; ++d) ks.group_mult[ps][d] = gp_mult(ord[ps], d, NGL, EPB);
+    return ks;
+}
+
 }  // namespace jx
