@@ -352,7 +352,7 @@ extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *c
     const int np = c->np, q = c->neqs;
     const int64_t total = E * np;
     const size_t nq = (size_t)N * q;
-    const bool grouped = c->ks->rec_layout == 4;      // group records (k_elem_gpencil)
+    const bool grouped = c->ks->rec_layout >= 4;      // group records (4: k_elem_gpencil, 5: k_elem_team)
     const int64_t ngroups = grouped ? (E + c->ks->elems_per_block - 1) / c->ks->elems_per_block : 0;
     const size_t rec_total = grouped ? (size_t)ngroups * c->ks->group_bytes : (size_t)E * c->rec_bytes;
     int rc;
@@ -396,7 +396,7 @@ extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *c
         GroupRetileArgs ga;
         ga.src = nullptr; ga.omega = d_omega; ga.Minv = c->Minv; ga.connijk = d_conn; ga.rec = c->rec; ga.nelem = E;
         ga.ngl = c->ngl; ga.epb = ks->elems_per_block; ga.nt = ks->group_nt; ga.group_bytes = ks->group_bytes;
-        ga.zid_off = ks->zid_off; ga.fid_off = ks->fid_off;
+        ga.zid_off = ks->zid_off; ga.fid_off = ks->fid_off; ga.layout = ks->rec_layout; ga.z_off = ks->z_off;
         for (int ps = 0; ps < 3; ++ps)
             for (int d = 0; d < 3; ++d) ga.mult[ps][d] = ks->group_mult[ps][d];
         CKC(cudaMemsetAsync(c->rec, 0, rec_total, c->stream));

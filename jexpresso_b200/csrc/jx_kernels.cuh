@@ -985,9 +985,7 @@ k_elem_wpencil(const __grid_constant__ ElemArgs a) {
 //     barrier less per equation and no read-modify-write of a partial;
 //   * the group record holds the metric terms as lane-major streams per pass (one coalesced LDG per stream),
 //     the node ids in the zeta-pass and flux-phase views, the quadrature weight omega*J and its pre-folded,
-//     negated product with M^-1 (atomics mode: no M^-1 gather, no "0 -" per output); the flux phase walks the
-//     group's nodes with (i, element slot) fastest, so the q gathers and the zeta-pass RED.ADDs of x-adjacent
-//     elements fall into the same 128-byte lines.
+//     negated product with M^-1 (atomics mode: no M^-1 gather, no "0 -" per output).
 // Arithmetic per output is the same IEEE sequence as k_elem_node / the oracle (deterministic mode:
 // bit-identical; atomics mode: identical up to the sign of zero and the order of the DSS sum).
 // ------------------------------------------------------------------------------------------
@@ -1046,6 +1044,8 @@ struct GroupRetileArgs {
     int ngl, epb, nt, group_bytes, zid_off, fid_off;
     int mult[3][3];           // [pass xi/eta/zeta][digit s/c0/c1]
     int slot;                 // 0..8 metric term, 9 = Je (stored as omega*J), -1 = node ids, -2 = -(omega*J*Minv)
+    int layout;               // 4: k_elem_gpencil group records; 5: k_elem_team records (z_off = zeta streams)
+    int z_off;
 };
 
 // element-fastest Julia arrays -> group records; thread = (element, local node), element fastest
@@ -1066,10 +1066,33 @@ static __global__ void k_retile_group(GroupRetileArgs a) {
     const int pet = s * a.mult[1][0] + i * a.mult[1][1] + k * a.mult[1][2];    // eta-pencil (i,k), node j
     const int pze = s * a.mult[2][0] + i * a.mult[2][1] + j * a.mult[2][2];    // zeta-pencil (i,j), node k
     const size_t src = (size_t)iel + (size_t)a.nelem * l;
+    if (a.layout == 5) {
+        // team records (k_elem_team): plane lane = k + n*(X + 3*s) holds xi_X, eta_X of plane k (streams n*j+i and
+        // n*n + n*j+i); zeta lane c = i + n*j of round s holds zeta_{x,y,z}, omega*J, -(omega*J*Minv) at node k
+        const int nc = n * n, nstrz = 5 * n, c = i + n * j;
+        double *zs = reinterpret_cast<double *>(rec + a.z_off) + (size_t)s * nstrz * 32;
+        if (a.slot == -1) {
+            const int32_t ip = (int32_t)(a.connijk[src] - 1);
+            zid[(s * n + k) * 32 + c] = ip;
+            fid[s * np + l] = ip;
+        } else if (a.slot == -2) {
+            const int32_t ip = zid[(s * n + k) * 32 + c];
+            zs[(4 * n + k) * 32 + c] = -(zs[(3 * n + k) * 32 + c] * a.Minv[ip]);
+        } else if (a.slot < 6) {
+            const int X = a.slot % 3, lane = k + n * (X + 3 * s);
+            met[(size_t)((a.slot < 3 ? 0 : nc) + n * j + i) * 32 + lane] = a.src[src];
+        } else if (a.slot < 9) {
+            zs[((a.slot - 6) * n + k) * 32 + c] = a.src[src];
+        } else {
+            const double wjk = a.omega[j] * a.omega[k];      // rhs.jl:1636-1643
+            zs[(3 * n + k) * 32 + c] = a.omega[i] * wjk * a.src[src];
+        }
+        return;
+    }
     if (a.slot == -1) {
         const int32_t ip = (int32_t)(a.connijk[src] - 1);
         zid[k * a.nt + pze] = ip;
-        fid[i + n * (s + a.epb * (j + n * k))] = ip;     // flux-phase order: (i, slot) fastest -> x-adjacent elements coalesce
+        fid[s * np + l] = ip;
     } else if (a.slot == -2) {
         const int32_t ip = zid[k * a.nt + pze];
         const double wJ = met[(size_t)(9 * n + k) * a.nt + pze];
@@ -1144,8 +1167,7 @@ k_elem_gpencil(const __grid_constant__ ElemArgs a) {
         bool nv[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int n = r * NT + t;
-            nv[r] = n < C::NNODE && (n / N) % EPB < cnt;
+            nv[r] = r * NT + t < cnt * NP;
             const int64_t node = nv[r] ? fidn[r] : 0;
 #pragma unroll
             for (int e = 0; e < NQ; ++e) qa[r][e] = nv[r] ? __ldg(a.u + (size_t)e * a.npoin + node) : 1.0;
@@ -1181,8 +1203,12 @@ k_elem_gpencil(const __grid_constant__ ElemArgs a) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (nv[r]) {
-                const int n = r * NT + t;          // group node n = i + N*(slot + EPB*(j + N*k))
-                const int ad = ((n / N) % EPB) * ES + (n % N) + PJ * ((n / (N * EPB)) % N) + PK * (n / (NC * EPB));
+                const int n = r * NT + t;          // group node n = slot*NP + l
+                int ad = n;
+                if constexpr (!C::PLAIN) {
+                    const int sl = n / NP, l = n % NP;
+                    ad = sl * ES + (l % N) + PJ * ((l / N) % N) + PK * (l / NC);
+                }
                 double q[NEQ], ax[EQ::NAUX], f[NEQ], gg[NEQ], h[NEQ];
 #pragma unroll
                 for (int e = 0; e < NEQ; ++e) q[e] = e < NQ ? qa[r][e < NQ ? e : 0] : 1.0;
@@ -1267,6 +1293,259 @@ k_elem_gpencil(const __grid_constant__ ElemArgs a) {
     }
 #undef JX_D
 #undef JX_DERIV_ALL
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused per-element kernel, variant "team" (3D, inviscid, exact order): two specialised warps per CTA work on a
+// group of EPB elements (2 at nop=4).  profiles/r01f: the pencil kernels are bound by the LSU data pipe --
+// 24 doubles cross shared memory per node and equation (9 line loads, 12 partial-product exchanges, 3 flux
+// stores).  Here
+//   * the PLANE warp: lane (slot, X in {F,G,H}, k) keeps the 25 values of plane k of field X_e in registers and
+//     computes BOTH in-plane derivatives from them (25 loads feed 250 FMAs), combines them with its register-
+//     resident metric terms xi_X, eta_X and writes the exact partial  B_X = dX/dxi*xi_X + dX/deta*eta_X
+//     (rhs.jl:1679-1687, first two products of each sum, left to right);
+//   * the ZETA warp: lane (i,j) of each element adds the zeta term from its line, (B_X + dX/dzeta*zeta_X),
+//     sums F,G,H parts left to right, applies the source and the quadrature weight and scatters (RED.ADD or
+//     rhs_el store) -- the reference's order, bit for bit;
+//   * the two roles run skewed by one equation on double-buffered B tiles: one block barrier per equation,
+//     15 doubles per node and equation through shared memory instead of 24;
+//   * flux tiles are ordered (equation, X) and padded to GB = 3 (mod 16) doubles so the 30 plane lanes of a
+//     warp-wide access fall on every bank pair at most twice (scripts/analysis/bank_search_team.py).
+// ------------------------------------------------------------------------------------------
+#ifndef JX_TEAM_MAXREG
+#define JX_TEAM_MAXREG 200      // 5 two-warp CTAs per SM (5 * 64 * 200 = 64000 registers)
+#endif
+template <int NGL, class EQ>
+struct ElemTeamCfg {
+    static constexpr int N = NGL, NC = NGL * NGL, NP = NGL * NGL * NGL, NEQ = EQ::NEQ;
+    static constexpr int EPB = 32 / (3 * NGL);                  // elements per group: 3*N*EPB plane lanes <= 32
+    static_assert(EPB >= 1 && NC <= 32, "team kernel: nop <= 4");
+    static constexpr int NPL = 3 * NGL * EPB;
+    static constexpr int NT = 64;
+    static constexpr int NNODE = EPB * NP;
+    static constexpr int R = (NNODE + NT - 1) / NT;
+    static constexpr int GB = (EPB * NP + 12) / 16 * 16 + 3;    // >= EPB*NP, = 3 (mod 16)
+    static constexpr int NFLD = 3 * NEQ;
+    static constexpr int NTILE = NFLD + 6 + (EQ::SRC_EQ >= 0 ? 1 : 0);
+    static constexpr size_t SMEM_BYTES = (size_t)NTILE * GB * 8;
+    static constexpr int NQ = EQ::NEQ - (EQ::FLUX_QMASK == ((1u << (EQ::NEQ - 1)) - 1u) ? 1 : 0);
+    static constexpr int NCOMP = NQ + EQ::NAUX;
+    static constexpr int NSTRZ = 5 * NGL;
+    static constexpr int Z_OFF = 2 * NC * 32 * 8;
+    static constexpr int ZID_OFF = Z_OFF + EPB * NSTRZ * 32 * 8;
+    static constexpr int FID_OFF = ZID_OFF + EPB * NGL * 32 * 4;
+    static constexpr int GROUP_BYTES = round_up(FID_OFF + R * NT * 4, 128);
+    static constexpr int MINB = (int)(233472 / (SMEM_BYTES + 1024)) < 5 ? (int)(233472 / (SMEM_BYTES + 1024)) : 5;
+};
+
+template <int NGL, class EQ>
+static __global__ void __maxnreg__(JX_TEAM_MAXREG)
+k_elem_team(const __grid_constant__ ElemArgs a) {
+    using C = ElemTeamCfg<NGL, EQ>;
+    constexpr int N = NGL, NC = C::NC, NP = C::NP, NEQ = C::NEQ, NT = C::NT, R = C::R, GB = C::GB, EPB = C::EPB;
+    constexpr int NQ = C::NQ, NCOMP = C::NCOMP, NSTRZ = C::NSTRZ;
+    static_assert(EQ::SRC_EQ >= -1, "pencil kernels keep at most one source component");
+    static_assert(EQ::HAS_AUX, "the pencil kernels use the two-stage flux functors");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *X = reinterpret_cast<double *>(smem_raw);     // [NEQ][3][GB]: F_e, G_e, H_e adjacent
+    double *B = X + (size_t)C::NFLD * GB;                 // [2][3][GB]
+    double *Sf = B + 6 * GB;                              // [GB]
+
+    const int t = threadIdx.x, lane = t & 31;
+    const bool plane_warp = t < 32;
+    // plane role: lane = k + N*(X + 3*slot)
+    const int pk = lane % N, pX = (lane / N) % 3, ps = lane / (3 * N);
+    const bool pact = lane < C::NPL;
+    const int poff = ps * NP + NC * pk;                   // plane k of element slot ps inside a tile
+    // zeta role: lane c = i + N*j
+    const bool zact = lane < NC;
+    const int c = zact ? lane : 0;
+    const bool fold = a.atomics && a.Minv != nullptr;
+#define JX_D(m, i) a.dpsi[(m) + NGL * (i)]
+    const int64_t ngroups = (a.nelem + EPB - 1) / EPB;
+    auto fid_of = [&](int64_t g) { return reinterpret_cast<const int32_t *>(a.rec + (size_t)g * C::GROUP_BYTES + C::FID_OFF); };
+    int fidn[R];
+    if ((int64_t)blockIdx.x < ngroups) {
+        const int32_t *fi = fid_of(blockIdx.x);
+#pragma unroll
+        for (int r = 0; r < R; ++r) fidn[r] = __ldcs(fi + r * NT + t);
+    }
+    // ---- pieces shared by the two roles (inlined into each role's branch so that every role has its own
+    //      register allocation: the plane metrics and the zeta metrics never coexist) -----------------------
+    auto issue_gathers = [&](int cnt, const int(&fid)[R], double(&qa)[R][NCOMP], bool(&nv)[R]) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            nv[r] = r * NT + t < cnt * NP;
+            const int64_t node = nv[r] ? fid[r] : 0;
+#pragma unroll
+            for (int e = 0; e < NQ; ++e) qa[r][e] = nv[r] ? __ldg(a.u + (size_t)e * a.npoin + node) : 1.0;
+#pragma unroll
+            for (int x = 0; x < EQ::NAUX; ++x) qa[r][NQ + x] = nv[r] ? __ldg(a.aux + (size_t)x * a.npoin + node) : 1.0;
+        }
+    };
+    auto prefetch_next = [&](int64_t gn, int(&fid)[R]) {   // next group: flux-view node ids -> registers, record -> L2
+        if (gn < ngroups) {
+            const int32_t *fi = fid_of(gn);
+#pragma unroll
+            for (int r = 0; r < R; ++r) fid[r] = __ldcs(fi + r * NT + t);
+            constexpr int CH = 1024;
+            for (int off = t * CH; off < C::FID_OFF; off += NT * CH)
+                prefetch_l2_bulk(a.rec + (size_t)gn * C::GROUP_BYTES + off, (C::FID_OFF - off) < CH ? (C::FID_OFF - off) : CH);
+        }
+    };
+    // flux / source at every node of the group, node-parallel (group node n = slot*NP + l)
+    auto flux_phase = [&](const double(&qa)[R][NCOMP], const bool(&nv)[R]) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (nv[r]) {
+                const int ad = r * NT + t;
+                double q[NEQ], ax[EQ::NAUX], f[NEQ], gg[NEQ], h[NEQ];
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e) q[e] = e < NQ ? qa[r][e < NQ ? e : 0] : 1.0;
+#pragma unroll
+                for (int x = 0; x < EQ::NAUX; ++x) ax[x] = qa[r][NQ + x];
+                EQ::flux_aux(a.phys, q, ax, f, gg, h);
+#pragma unroll
+                for (int e = 0; e < NEQ; ++e) {
+                    X[(e * 3 + 0) * GB + ad] = f[e];
+                    X[(e * 3 + 1) * GB + ad] = gg[e];
+                    X[(e * 3 + 2) * GB + ad] = h[e];
+                }
+                if constexpr (EQ::SRC_EQ >= 0) Sf[ad] = a.lsource ? EQ::source_aux(a.phys, q, ax) : 0.0;
+            }
+        }
+    };
+    // block barrier reached from both role branches (bar.sync counts warps, not program locations)
+    auto block_sync = [&]() { asm volatile("bar.sync 0;" ::: "memory"); };
+
+    if (plane_warp) {
+        // =============================== PLANE ROLE ===============================
+        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+            const int cnt = (int)(a.nelem - g * EPB < EPB ? a.nelem - g * EPB : EPB);
+            const double *pl = reinterpret_cast<const double *>(a.rec + (size_t)g * C::GROUP_BYTES);
+            double qa[R][NCOMP];
+            bool nv[R];
+            issue_gathers(cnt, fidn, qa, nv);
+            double mxi[NC], met[NC];             // xi_X, eta_X at the 25 nodes of plane k (lane-major streams)
+#pragma unroll
+            for (int n = 0; n < NC; ++n) { mxi[n] = __ldcs(pl + n * 32 + lane); met[n] = __ldcs(pl + (NC + n) * 32 + lane); }
+            prefetch_next(g + gridDim.x, fidn);
+            flux_phase(qa, nv);
+            block_sync();
+            const bool live = pact && ps < cnt;
+#pragma unroll 1
+            for (int step = 0; step <= NEQ; ++step) {
+                if (step < NEQ && live) {
+                    const double *T = X + (size_t)(step * 3 + pX) * GB + poff;
+                    double *Bo = B + (size_t)((step & 1) * 3 + pX) * GB + poff;
+                    double v[NC];
+#pragma unroll
+                    for (int n = 0; n < NC; ++n) v[n] = T[n];
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        double dx[N], de[N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) { dx[i] = 0.0; de[i] = 0.0; }
+#pragma unroll
+                        for (int m = 0; m < N; ++m)
+#pragma unroll
+                            for (int i = 0; i < N; ++i) {
+                                dx[i] = fma(JX_D(m, i), v[N * j + m], dx[i]);
+                                de[i] = fma(JX_D(m, j), v[N * m + i], de[i]);
+                            }
+#pragma unroll
+                        for (int i = 0; i < N; ++i) Bo[N * j + i] = dx[i] * mxi[N * j + i] + de[i] * met[N * j + i];
+                    }
+                }
+                block_sync();   // B[step&1] complete; the zeta warp is done with B[(step-1)&1]
+            }
+        }
+    } else {
+        // =============================== ZETA ROLE ===============================
+        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+            const int64_t e0 = g * EPB;
+            const int cnt = (int)(a.nelem - e0 < EPB ? a.nelem - e0 : EPB);
+            const char *rec = a.rec + (size_t)g * C::GROUP_BYTES;
+            const double *zs = reinterpret_cast<const double *>(rec + C::Z_OFF);
+            const int32_t *zid = reinterpret_cast<const int32_t *>(rec + C::ZID_OFF);
+            double qa[R][NCOMP];
+            bool nv[R];
+            issue_gathers(cnt, fidn, qa, nv);
+            double mz[EPB][3][N], wj[EPB][N];
+            int ip[EPB][N];
+#pragma unroll
+            for (int s = 0; s < EPB; ++s) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int m = 0; m < N; ++m) mz[s][q][m] = __ldcs(zs + (s * NSTRZ + q * N + m) * 32 + lane);
+#pragma unroll
+                for (int m = 0; m < N; ++m) {
+                    wj[s][m] = __ldcs(zs + (s * NSTRZ + (fold ? 4 : 3) * N + m) * 32 + lane);
+                    ip[s][m] = __ldcs(zid + (s * N + m) * 32 + lane);
+                }
+            }
+            prefetch_next(g + gridDim.x, fidn);
+            flux_phase(qa, nv);
+            block_sync();
+#pragma unroll 1
+            for (int step = 0; step <= NEQ; ++step) {
+                if (step >= 1) {
+                    const int e = step - 1;
+#pragma unroll
+                    for (int s = 0; s < EPB; ++s) {
+                        if (zact && s < cnt) {
+                            const double *Fe = X + (size_t)(e * 3) * GB + s * NP + c, *Ge = Fe + GB, *He = Ge + GB;
+                            const double *Bf = B + (size_t)((e & 1) * 3) * GB + s * NP + c;
+                            double f[N], gg[N], h[N], b[3][N], Sv[N];
+#pragma unroll
+                            for (int m = 0; m < N; ++m) { f[m] = Fe[NC * m]; gg[m] = Ge[NC * m]; h[m] = He[NC * m]; }
+#pragma unroll
+                            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                                for (int k = 0; k < N; ++k) b[q][k] = Bf[q * GB + NC * k];
+#pragma unroll
+                            for (int k = 0; k < N; ++k) Sv[k] = 0.0;
+                            if constexpr (EQ::SRC_EQ >= 0) {
+                                if (e == EQ::SRC_EQ) {
+#pragma unroll
+                                    for (int k = 0; k < N; ++k) Sv[k] = Sf[s * NP + c + NC * k];
+                                }
+                            }
+                            double dF[N], dG[N], dH[N];
+#pragma unroll
+                            for (int o = 0; o < N; ++o) { dF[o] = 0.0; dG[o] = 0.0; dH[o] = 0.0; }
+#pragma unroll
+                            for (int m = 0; m < N; ++m)
+#pragma unroll
+                                for (int o = 0; o < N; ++o) {
+                                    dF[o] = fma(JX_D(m, o), f[m], dF[o]);
+                                    dG[o] = fma(JX_D(m, o), gg[m], dG[o]);
+                                    dH[o] = fma(JX_D(m, o), h[m], dH[o]);
+                                }
+                            double *due = a.du + (size_t)e * a.npoin;
+                            double *rhe = a.atomics ? nullptr : a.rhs_el + ((size_t)(e0 + s) * NEQ + e) * NP + c;
+#pragma unroll
+                            for (int k = 0; k < N; ++k) {
+                                const double dFdx = b[0][k] + dF[k] * mz[s][0][k];
+                                const double dGdy = b[1][k] + dG[k] * mz[s][1][k];
+                                const double dHdz = b[2][k] + dH[k] * mz[s][2][k];
+                                const double r = (dFdx + dGdy) + dHdz;
+                                if (fold) atomicAdd(due + ip[s][k], wj[s][k] * (r - Sv[k]));     // wj = -(omega*J*Minv)
+                                else {
+                                    const double out = 0.0 - wj[s][k] * (r - Sv[k]);
+                                    if (rhe) rhe[NC * k] = out;
+                                    else atomicAdd(due + ip[s][k], out);
+                                }
+                            }
+                        }
+                    }
+                }
+                block_sync();
+            }
+        }
+    }
+#undef JX_D
 }
 
 // ------------------------------------------------------------------------------------------

@@ -185,4 +185,40 @@ KernelSet make_gpencil_set(int eq_id, int lpert, int jxpow, int variant) {
     return ks;
 }
 
+// variant 7: two specialised warps (plane role + zeta-pencil role) per element group, 3D inviscid, exact order
+template <int NGL, class EQ>
+struct TeamKernel {
+    using C = ElemTeamCfg<NGL, EQ>;
+    static cudaError_t prepare() {
+        return cudaFuncSetAttribute(k_elem_team<NGL, EQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    }
+    static int max_blocks() {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_team<NGL, EQ>, C::NT, C::SMEM_BYTES);
+        return nb;
+    }
+    static void launch(const ElemArgs &a, int grid, cudaStream_t s) { k_elem_team<NGL, EQ><<<grid, C::NT, C::SMEM_BYTES, s>>>(a); }
+};
+
+template <int NGL, class EQ>
+KernelSet make_team_set(int eq_id, int lpert, int jxpow, int variant) {
+    using K = TeamKernel<NGL, EQ>;
+    using C = typename K::C;
+    KernelSet ks;
+    ks.nsd = 3; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = 0; ks.variant = variant;
+    ks.neq = EQ::NEQ;
+    ks.elems_per_block = C::EPB;
+    ks.rec_layout = 5;
+    ks.nthreads = C::NT;
+    ks.smem_bytes = C::SMEM_BYTES;
+    ks.prepare = &K::prepare;
+    ks.max_blocks_per_sm = &K::max_blocks;
+    ks.launch_elem = &K::launch;
+    ks.launch_bc = &launch_bc_t<EQ>;
+    ks.launch_gather = &launch_gather_t<EQ::NEQ>;
+    ks.launch_aux = &launch_aux_t<EQ>;
+    ks.group_bytes = C::GROUP_BYTES; ks.group_nt = 32; ks.zid_off = C::ZID_OFF; ks.fid_off = C::FID_OFF; ks.z_off = C::Z_OFF;
+    return ks;
+}
+
 }  // namespace jx
