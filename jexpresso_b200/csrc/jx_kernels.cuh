@@ -1296,7 +1296,7 @@ k_elem_gpencil(const __grid_constant__ ElemArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Fused per-element kernel, variant "team" (3D, inviscid, exact order): two specialised warps per CTA work on a
+// Fused per-element kernel, variant "team" (3D, inviscid, exact order): specialised warps of one CTA work on a
 // group of EPB elements (2 at nop=4).  profiles/r01f: the pencil kernels are bound by the LSU data pipe --
 // 24 doubles cross shared memory per node and equation (9 line loads, 12 partial-product exchanges, 3 flux
 // stores).  Here
@@ -1312,16 +1312,18 @@ k_elem_gpencil(const __grid_constant__ ElemArgs a) {
 //   * flux tiles are ordered (equation, X) and padded to GB = 3 (mod 16) doubles so the 30 plane lanes of a
 //     warp-wide access fall on every bank pair at most twice (scripts/analysis/bank_search_team.py).
 // ------------------------------------------------------------------------------------------
-#ifndef JX_TEAM_MAXREG
-#define JX_TEAM_MAXREG 200      // 5 two-warp CTAs per SM (5 * 64 * 200 = 64000 registers)
-#endif
-template <int NGL, class EQ>
+// ZW = number of zeta-role warps (1: one warp walks all element slots; EPB: one warp per slot).
+// MODE = 0: rhs_el store (deterministic DSS); 1: RED.ADD of omega*J-weighted values; 2: RED.ADD with M^-1 pre-folded
+template <int NGL, class EQ, int ZW = 1, int RG = 0>
 struct ElemTeamCfg {
     static constexpr int N = NGL, NC = NGL * NGL, NP = NGL * NGL * NGL, NEQ = EQ::NEQ;
     static constexpr int EPB = 32 / (3 * NGL);                  // elements per group: 3*N*EPB plane lanes <= 32
     static_assert(EPB >= 1 && NC <= 32, "team kernel: nop <= 4");
     static constexpr int NPL = 3 * NGL * EPB;
-    static constexpr int NT = 64;
+    static_assert(ZW == 1 || ZW == EPB, "one zeta warp, or one per element slot");
+    static constexpr int SPW = EPB / ZW;                        // element slots per zeta warp
+    static constexpr int NT = 32 * (1 + ZW);
+    static constexpr int MAXREG = RG == 1 ? 224 : (NT == 64 ? 200 : 168);   // RG 0: 4-5 CTAs per SM; RG 1: 3 CTAs, no spills
     static constexpr int NNODE = EPB * NP;
     static constexpr int R = (NNODE + NT - 1) / NT;
     static constexpr int GB = (EPB * NP + 12) / 16 * 16 + 3;    // >= EPB*NP, = 3 (mod 16)
@@ -1334,14 +1336,14 @@ struct ElemTeamCfg {
     static constexpr int Z_OFF = 2 * NC * 32 * 8;
     static constexpr int ZID_OFF = Z_OFF + EPB * NSTRZ * 32 * 8;
     static constexpr int FID_OFF = ZID_OFF + EPB * NGL * 32 * 4;
-    static constexpr int GROUP_BYTES = round_up(FID_OFF + R * NT * 4, 128);
-    static constexpr int MINB = (int)(233472 / (SMEM_BYTES + 1024)) < 5 ? (int)(233472 / (SMEM_BYTES + 1024)) : 5;
+    static constexpr int GROUP_BYTES = round_up(FID_OFF + NNODE * 4, 128);
 };
 
-template <int NGL, class EQ>
-static __global__ void __maxnreg__(JX_TEAM_MAXREG)
+template <int NGL, class EQ, int ZW, int MODE, int RG>
+static __global__ void __maxnreg__((ElemTeamCfg<NGL, EQ, ZW, RG>::MAXREG))
 k_elem_team(const __grid_constant__ ElemArgs a) {
-    using C = ElemTeamCfg<NGL, EQ>;
+    using C = ElemTeamCfg<NGL, EQ, ZW, RG>;
+    constexpr int SPW = C::SPW;
     constexpr int N = NGL, NC = C::NC, NP = C::NP, NEQ = C::NEQ, NT = C::NT, R = C::R, GB = C::GB, EPB = C::EPB;
     constexpr int NQ = C::NQ, NCOMP = C::NCOMP, NSTRZ = C::NSTRZ;
     static_assert(EQ::SRC_EQ >= -1, "pencil kernels keep at most one source component");
@@ -1360,7 +1362,8 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
     // zeta role: lane c = i + N*j
     const bool zact = lane < NC;
     const int c = zact ? lane : 0;
-    const bool fold = a.atomics && a.Minv != nullptr;
+    const int zw = (t >> 5) - 1;                          // zeta warp index (role branch only)
+    constexpr bool fold = MODE == 2;
 #define JX_D(m, i) a.dpsi[(m) + NGL * (i)]
     const int64_t ngroups = (a.nelem + EPB - 1) / EPB;
     auto fid_of = [&](int64_t g) { return reinterpret_cast<const int32_t *>(a.rec + (size_t)g * C::GROUP_BYTES + C::FID_OFF); };
@@ -1368,10 +1371,12 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
     if ((int64_t)blockIdx.x < ngroups) {
         const int32_t *fi = fid_of(blockIdx.x);
 #pragma unroll
-        for (int r = 0; r < R; ++r) fidn[r] = __ldcs(fi + r * NT + t);
+        for (int r = 0; r < R; ++r) fidn[r] = r * NT + t < C::NNODE ? __ldcs(fi + r * NT + t) : 0;
     }
-    // ---- pieces shared by the two roles (inlined into each role's branch so that every role has its own
-    //      register allocation: the plane metrics and the zeta metrics never coexist) -----------------------
+    // ---- pieces shared by the roles (inlined into each role's branch so that every role has its own register
+    //      allocation: the plane metrics and the zeta metrics never coexist).  All warps take part in the flux
+    //      phase: giving it to the zeta warps alone (with the next group's gathers held in their registers) was
+    //      measured 35 % slower (profiles/r01f) -- the flux arithmetic, not the gather latency, is what counts.
     auto issue_gathers = [&](int cnt, const int(&fid)[R], double(&qa)[R][NCOMP], bool(&nv)[R]) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -1387,7 +1392,7 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
         if (gn < ngroups) {
             const int32_t *fi = fid_of(gn);
 #pragma unroll
-            for (int r = 0; r < R; ++r) fid[r] = __ldcs(fi + r * NT + t);
+            for (int r = 0; r < R; ++r) fid[r] = r * NT + t < C::NNODE ? __ldcs(fi + r * NT + t) : 0;
             constexpr int CH = 1024;
             for (int off = t * CH; off < C::FID_OFF; off += NT * CH)
                 prefetch_l2_bulk(a.rec + (size_t)gn * C::GROUP_BYTES + off, (C::FID_OFF - off) < CH ? (C::FID_OFF - off) : CH);
@@ -1457,7 +1462,7 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
                         for (int i = 0; i < N; ++i) Bo[N * j + i] = dx[i] * mxi[N * j + i] + de[i] * met[N * j + i];
                     }
                 }
-                block_sync();   // B[step&1] complete; the zeta warp is done with B[(step-1)&1]
+                block_sync();   // B[step&1] complete; the zeta warps are done with B[(step-1)&1]
             }
         }
     } else {
@@ -1471,18 +1476,19 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
             double qa[R][NCOMP];
             bool nv[R];
             issue_gathers(cnt, fidn, qa, nv);
-            double mz[EPB][3][N], wj[EPB][N];
-            int ip[EPB][N];
+            double mz[SPW][3][N], wj[SPW][N];
+            int ip[SPW][N];
 #pragma unroll
-            for (int s = 0; s < EPB; ++s) {
+            for (int sl = 0; sl < SPW; ++sl) {
+                const int s = zw * SPW + sl;
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
 #pragma unroll
-                    for (int m = 0; m < N; ++m) mz[s][q][m] = __ldcs(zs + (s * NSTRZ + q * N + m) * 32 + lane);
+                    for (int m = 0; m < N; ++m) mz[sl][q][m] = __ldcs(zs + (s * NSTRZ + q * N + m) * 32 + lane);
 #pragma unroll
                 for (int m = 0; m < N; ++m) {
-                    wj[s][m] = __ldcs(zs + (s * NSTRZ + (fold ? 4 : 3) * N + m) * 32 + lane);
-                    ip[s][m] = __ldcs(zid + (s * N + m) * 32 + lane);
+                    wj[sl][m] = __ldcs(zs + (s * NSTRZ + (fold ? 4 : 3) * N + m) * 32 + lane);
+                    ip[sl][m] = __ldcs(zid + (s * N + m) * 32 + lane);
                 }
             }
             prefetch_next(g + gridDim.x, fidn);
@@ -1493,7 +1499,8 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
                 if (step >= 1) {
                     const int e = step - 1;
 #pragma unroll
-                    for (int s = 0; s < EPB; ++s) {
+                    for (int sl = 0; sl < SPW; ++sl) {
+                        const int s = zw * SPW + sl;
                         if (zact && s < cnt) {
                             const double *Fe = X + (size_t)(e * 3) * GB + s * NP + c, *Ge = Fe + GB, *He = Ge + GB;
                             const double *Bf = B + (size_t)((e & 1) * 3) * GB + s * NP + c;
@@ -1524,18 +1531,18 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
                                     dH[o] = fma(JX_D(m, o), h[m], dH[o]);
                                 }
                             double *due = a.du + (size_t)e * a.npoin;
-                            double *rhe = a.atomics ? nullptr : a.rhs_el + ((size_t)(e0 + s) * NEQ + e) * NP + c;
+                            double *rhe = MODE == 0 ? a.rhs_el + ((size_t)(e0 + s) * NEQ + e) * NP + c : nullptr;
 #pragma unroll
                             for (int k = 0; k < N; ++k) {
-                                const double dFdx = b[0][k] + dF[k] * mz[s][0][k];
-                                const double dGdy = b[1][k] + dG[k] * mz[s][1][k];
-                                const double dHdz = b[2][k] + dH[k] * mz[s][2][k];
+                                const double dFdx = b[0][k] + dF[k] * mz[sl][0][k];
+                                const double dGdy = b[1][k] + dG[k] * mz[sl][1][k];
+                                const double dHdz = b[2][k] + dH[k] * mz[sl][2][k];
                                 const double r = (dFdx + dGdy) + dHdz;
-                                if (fold) atomicAdd(due + ip[s][k], wj[s][k] * (r - Sv[k]));     // wj = -(omega*J*Minv)
+                                if constexpr (MODE == 2) atomicAdd(due + ip[sl][k], wj[sl][k] * (r - Sv[k]));   // wj = -(omega*J*Minv)
                                 else {
-                                    const double out = 0.0 - wj[s][k] * (r - Sv[k]);
-                                    if (rhe) rhe[NC * k] = out;
-                                    else atomicAdd(due + ip[s][k], out);
+                                    const double out = 0.0 - wj[sl][k] * (r - Sv[k]);
+                                    if constexpr (MODE == 0) rhe[NC * k] = out;
+                                    else atomicAdd(due + ip[sl][k], out);
                                 }
                             }
                         }

@@ -185,24 +185,33 @@ KernelSet make_gpencil_set(int eq_id, int lpert, int jxpow, int variant) {
     return ks;
 }
 
-// variant 7: two specialised warps (plane role + zeta-pencil role) per element group, 3D inviscid, exact order
-template <int NGL, class EQ>
+// variant 7 (one zeta warp) / 8 (one zeta warp per element slot): plane-role + zeta-pencil-role warp team per element
+// group, 3D inviscid, exact order; the scatter mode (rhs_el store / RED.ADD / RED.ADD with folded M^-1) is a
+// template parameter chosen per launch
+template <int NGL, class EQ, int ZW, int RG>
 struct TeamKernel {
-    using C = ElemTeamCfg<NGL, EQ>;
+    using C = ElemTeamCfg<NGL, EQ, ZW, RG>;
     static cudaError_t prepare() {
-        return cudaFuncSetAttribute(k_elem_team<NGL, EQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_elem_team<NGL, EQ, ZW, 0, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_team<NGL, EQ, ZW, 1, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_team<NGL, EQ, ZW, 2, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        return e;
     }
     static int max_blocks() {
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_team<NGL, EQ>, C::NT, C::SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_team<NGL, EQ, ZW, 2, RG>, C::NT, C::SMEM_BYTES);
         return nb;
     }
-    static void launch(const ElemArgs &a, int grid, cudaStream_t s) { k_elem_team<NGL, EQ><<<grid, C::NT, C::SMEM_BYTES, s>>>(a); }
+    static void launch(const ElemArgs &a, int grid, cudaStream_t s) {
+        if (!a.atomics) k_elem_team<NGL, EQ, ZW, 0, RG><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+        else if (a.Minv == nullptr) k_elem_team<NGL, EQ, ZW, 1, RG><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+        else k_elem_team<NGL, EQ, ZW, 2, RG><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+    }
 };
 
-template <int NGL, class EQ>
+template <int NGL, class EQ, int ZW, int RG>
 KernelSet make_team_set(int eq_id, int lpert, int jxpow, int variant) {
-    using K = TeamKernel<NGL, EQ>;
+    using K = TeamKernel<NGL, EQ, ZW, RG>;
     using C = typename K::C;
     KernelSet ks;
     ks.nsd = 3; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = 0; ks.variant = variant;
