@@ -26,14 +26,14 @@ namespace jx {
     JX_GSET(NGL, EPB, VAR, false, false), JX_GSET(NGL, EPB, VAR, false, true), JX_GSET(NGL, EPB, VAR, true, false), \
     JX_GSET(NGL, EPB, VAR, true, true)
 
-#define JX_TSET(NGL, ZW, RG, VAR, PERT, POW) make_team_set<NGL, EulerTheta<3, PERT, POW>, ZW, RG>(JX_EQ_EULER_THETA, PERT, POW, VAR)
-#define JX_TROW(NGL, ZW, RG, VAR) \
-    JX_TSET(NGL, ZW, RG, VAR, false, false), JX_TSET(NGL, ZW, RG, VAR, false, true), JX_TSET(NGL, ZW, RG, VAR, true, false), \
-    JX_TSET(NGL, ZW, RG, VAR, true, true)
+#define JX_TSET(NGL, ZW, PW, VAR, PERT, POW) make_team_set<NGL, EulerTheta<3, PERT, POW>, ZW, PW>(JX_EQ_EULER_THETA, PERT, POW, VAR)
+#define JX_TROW(NGL, ZW, PW, VAR) \
+    JX_TSET(NGL, ZW, PW, VAR, false, false), JX_TSET(NGL, ZW, PW, VAR, false, true), JX_TSET(NGL, ZW, PW, VAR, true, false), \
+    JX_TSET(NGL, ZW, PW, VAR, true, true)
 
 const KernelSet *lookup_euler_theta_3d(int ngl, int lpert, int jxpow, int lvisc, int variant) {
     static const KernelSet table[] = {JX_ROW(3), JX_ROW(5), JX_ROW(6), JX_ROW(8), JX_PROW(3), JX_PROW(5), JX_WROW(3), JX_WROW(5), JX_WROW(6),
-                                      JX_GROW(3, 7, 5), JX_GROW(5, 5, 5), JX_GROW(5, 1, 6), JX_TROW(3, 3, 0, 8), JX_TROW(5, 2, 0, 8), JX_TROW(5, 2, 1, 9)};
+                                      JX_GROW(3, 7, 5), JX_GROW(5, 5, 5), JX_GROW(5, 1, 6), JX_TROW(3, 3, 1, 8), JX_TROW(5, 2, 1, 8), JX_TROW(5, 2, 2, 9)};
     for (const KernelSet &k : table)
         if (k.ngl == ngl && k.lpert == lpert && k.jxpow == jxpow && k.lvisc == lvisc && k.variant == variant) return &k;
     return nullptr;

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "jx_functors.cuh"
 
 namespace jx {
@@ -1314,7 +1316,7 @@ k_elem_gpencil(const __grid_constant__ ElemArgs a) {
 // ------------------------------------------------------------------------------------------
 // ZW = number of zeta-role warps (1: one warp walks all element slots; EPB: one warp per slot).
 // MODE = 0: rhs_el store (deterministic DSS); 1: RED.ADD of omega*J-weighted values; 2: RED.ADD with M^-1 pre-folded
-template <int NGL, class EQ, int ZW = 1, int RG = 0>
+template <int NGL, class EQ, int ZW = 1, int PW = 1>
 struct ElemTeamCfg {
     static constexpr int N = NGL, NC = NGL * NGL, NP = NGL * NGL * NGL, NEQ = EQ::NEQ;
     static constexpr int EPB = 32 / (3 * NGL);                  // elements per group: 3*N*EPB plane lanes <= 32
@@ -1322,8 +1324,10 @@ struct ElemTeamCfg {
     static constexpr int NPL = 3 * NGL * EPB;
     static_assert(ZW == 1 || ZW == EPB, "one zeta warp, or one per element slot");
     static constexpr int SPW = EPB / ZW;                        // element slots per zeta warp
-    static constexpr int NT = 32 * (1 + ZW);
-    static constexpr int MAXREG = RG == 1 ? 224 : (NT == 64 ? 200 : 168);   // RG 0: 4-5 CTAs per SM; RG 1: 3 CTAs, no spills
+    static_assert(PW == 1 || PW == 2, "one plane warp, or two sharing the nodes of every plane");
+    static constexpr int NT = 32 * (PW + ZW);
+    static constexpr int MAXREG = NT == 64 ? 200 : (NT == 96 ? 168 : 128);   // 4-5 CTAs per SM
+    static constexpr int NSPLIT = PW == 1 ? NC : (NC + 1) / 2;              // plane warp 0 owns nodes [0,NSPLIT), warp 1 the rest
     static constexpr int NNODE = EPB * NP;
     static constexpr int R = (NNODE + NT - 1) / NT;
     static constexpr int GB = (EPB * NP + 12) / 16 * 16 + 3;    // >= EPB*NP, = 3 (mod 16)
@@ -1339,10 +1343,10 @@ struct ElemTeamCfg {
     static constexpr int GROUP_BYTES = round_up(FID_OFF + NNODE * 4, 128);
 };
 
-template <int NGL, class EQ, int ZW, int MODE, int RG>
-static __global__ void __maxnreg__((ElemTeamCfg<NGL, EQ, ZW, RG>::MAXREG))
+template <int NGL, class EQ, int ZW, int MODE, int PW>
+static __global__ void __maxnreg__((ElemTeamCfg<NGL, EQ, ZW, PW>::MAXREG))
 k_elem_team(const __grid_constant__ ElemArgs a) {
-    using C = ElemTeamCfg<NGL, EQ, ZW, RG>;
+    using C = ElemTeamCfg<NGL, EQ, ZW, PW>;
     constexpr int SPW = C::SPW;
     constexpr int N = NGL, NC = C::NC, NP = C::NP, NEQ = C::NEQ, NT = C::NT, R = C::R, GB = C::GB, EPB = C::EPB;
     constexpr int NQ = C::NQ, NCOMP = C::NCOMP, NSTRZ = C::NSTRZ;
@@ -1354,7 +1358,7 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
     double *Sf = B + 6 * GB;                              // [GB]
 
     const int t = threadIdx.x, lane = t & 31;
-    const bool plane_warp = t < 32;
+    const bool plane_warp = t < 32 * PW;
     // plane role: lane = k + N*(X + 3*slot)
     const int pk = lane % N, pX = (lane / N) % 3, ps = lane / (3 * N);
     const bool pact = lane < C::NPL;
@@ -1362,7 +1366,7 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
     // zeta role: lane c = i + N*j
     const bool zact = lane < NC;
     const int c = zact ? lane : 0;
-    const int zw = (t >> 5) - 1;                          // zeta warp index (role branch only)
+    const int zw = (t >> 5) - PW;                         // zeta warp index (role branch only)
     constexpr bool fold = MODE == 2;
 #define JX_D(m, i) a.dpsi[(m) + NGL * (i)]
     const int64_t ngroups = (a.nelem + EPB - 1) / EPB;
@@ -1423,17 +1427,20 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
     // block barrier reached from both role branches (bar.sync counts warps, not program locations)
     auto block_sync = [&]() { asm volatile("bar.sync 0;" ::: "memory"); };
 
-    if (plane_warp) {
-        // =============================== PLANE ROLE ===============================
+    // plane role over the node range [LO, HI) of every plane (PW = 2: the two plane warps split the 25 outputs;
+    // both read the whole plane, each keeps only its own metric terms -> half the registers, half the step time)
+    auto plane_role = [&](auto lo_c, auto hi_c) {
+        constexpr int LO = decltype(lo_c)::value, HI = decltype(hi_c)::value, NN = HI - LO;
+        constexpr int CHUNK = 5;                 // outputs in flight: 2*CHUNK independent FMA chains
         for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
             const int cnt = (int)(a.nelem - g * EPB < EPB ? a.nelem - g * EPB : EPB);
             const double *pl = reinterpret_cast<const double *>(a.rec + (size_t)g * C::GROUP_BYTES);
             double qa[R][NCOMP];
             bool nv[R];
             issue_gathers(cnt, fidn, qa, nv);
-            double mxi[NC], met[NC];             // xi_X, eta_X at the 25 nodes of plane k (lane-major streams)
+            double mxi[NN], met[NN];             // xi_X, eta_X at this warp's nodes of plane k (lane-major streams)
 #pragma unroll
-            for (int n = 0; n < NC; ++n) { mxi[n] = __ldcs(pl + n * 32 + lane); met[n] = __ldcs(pl + (NC + n) * 32 + lane); }
+            for (int n = 0; n < NN; ++n) { mxi[n] = __ldcs(pl + (LO + n) * 32 + lane); met[n] = __ldcs(pl + (NC + LO + n) * 32 + lane); }
             prefetch_next(g + gridDim.x, fidn);
             flux_phase(qa, nv);
             block_sync();
@@ -1447,23 +1454,35 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
 #pragma unroll
                     for (int n = 0; n < NC; ++n) v[n] = T[n];
 #pragma unroll
-                    for (int j = 0; j < N; ++j) {
-                        double dx[N], de[N];
+                    for (int c0 = 0; c0 < NN; c0 += CHUNK) {
+                        double dx[CHUNK], de[CHUNK];
 #pragma unroll
-                        for (int i = 0; i < N; ++i) { dx[i] = 0.0; de[i] = 0.0; }
+                        for (int u = 0; u < CHUNK; ++u) { dx[u] = 0.0; de[u] = 0.0; }
 #pragma unroll
                         for (int m = 0; m < N; ++m)
 #pragma unroll
-                            for (int i = 0; i < N; ++i) {
-                                dx[i] = fma(JX_D(m, i), v[N * j + m], dx[i]);
-                                de[i] = fma(JX_D(m, j), v[N * m + i], de[i]);
+                            for (int u = 0; u < CHUNK; ++u) {
+                                if (c0 + u < NN) {
+                                    const int n = LO + c0 + u, i = n % N, j = n / N;
+                                    dx[u] = fma(JX_D(m, i), v[N * j + m], dx[u]);
+                                    de[u] = fma(JX_D(m, j), v[N * m + i], de[u]);
+                                }
                             }
 #pragma unroll
-                        for (int i = 0; i < N; ++i) Bo[N * j + i] = dx[i] * mxi[N * j + i] + de[i] * met[N * j + i];
+                        for (int u = 0; u < CHUNK; ++u)
+                            if (c0 + u < NN) Bo[LO + c0 + u] = dx[u] * mxi[c0 + u] + de[u] * met[c0 + u];
                     }
                 }
                 block_sync();   // B[step&1] complete; the zeta warps are done with B[(step-1)&1]
             }
+        }
+    };
+    if (plane_warp) {
+        // =============================== PLANE ROLE ===============================
+        if constexpr (PW == 1) plane_role(std::integral_constant<int, 0>{}, std::integral_constant<int, NC>{});
+        else {
+            if (t < 32) plane_role(std::integral_constant<int, 0>{}, std::integral_constant<int, C::NSPLIT>{});
+            else plane_role(std::integral_constant<int, C::NSPLIT>{}, std::integral_constant<int, NC>{});
         }
     } else {
         // =============================== ZETA ROLE ===============================

@@ -185,33 +185,33 @@ KernelSet make_gpencil_set(int eq_id, int lpert, int jxpow, int variant) {
     return ks;
 }
 
-// variant 7 (one zeta warp) / 8 (one zeta warp per element slot): plane-role + zeta-pencil-role warp team per element
+// variant 8 (one plane warp, one zeta warp per element slot) / 9 (two plane warps): plane-role + zeta-pencil-role warp team per element
 // group, 3D inviscid, exact order; the scatter mode (rhs_el store / RED.ADD / RED.ADD with folded M^-1) is a
 // template parameter chosen per launch
-template <int NGL, class EQ, int ZW, int RG>
+template <int NGL, class EQ, int ZW, int PW>
 struct TeamKernel {
-    using C = ElemTeamCfg<NGL, EQ, ZW, RG>;
+    using C = ElemTeamCfg<NGL, EQ, ZW, PW>;
     static cudaError_t prepare() {
-        cudaError_t e = cudaFuncSetAttribute(k_elem_team<NGL, EQ, ZW, 0, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_team<NGL, EQ, ZW, 1, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_team<NGL, EQ, ZW, 2, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_elem_team<NGL, EQ, ZW, 0, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_team<NGL, EQ, ZW, 1, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_team<NGL, EQ, ZW, 2, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
         return e;
     }
     static int max_blocks() {
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_team<NGL, EQ, ZW, 2, RG>, C::NT, C::SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_team<NGL, EQ, ZW, 2, PW>, C::NT, C::SMEM_BYTES);
         return nb;
     }
     static void launch(const ElemArgs &a, int grid, cudaStream_t s) {
-        if (!a.atomics) k_elem_team<NGL, EQ, ZW, 0, RG><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
-        else if (a.Minv == nullptr) k_elem_team<NGL, EQ, ZW, 1, RG><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
-        else k_elem_team<NGL, EQ, ZW, 2, RG><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+        if (!a.atomics) k_elem_team<NGL, EQ, ZW, 0, PW><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+        else if (a.Minv == nullptr) k_elem_team<NGL, EQ, ZW, 1, PW><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+        else k_elem_team<NGL, EQ, ZW, 2, PW><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
     }
 };
 
-template <int NGL, class EQ, int ZW, int RG>
+template <int NGL, class EQ, int ZW, int PW>
 KernelSet make_team_set(int eq_id, int lpert, int jxpow, int variant) {
-    using K = TeamKernel<NGL, EQ, ZW, RG>;
+    using K = TeamKernel<NGL, EQ, ZW, PW>;
     using C = typename K::C;
     KernelSet ks;
     ks.nsd = 3; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = 0; ks.variant = variant;
