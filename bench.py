@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--pert", action="store_true")
     ap.add_argument("--dss-mode", type=int, default=int(os.environ.get("JX_DSS_MODE", "1")))
     ap.add_argument("--pow-mode", type=int, default=int(os.environ.get("JX_POW_MODE", "1")))
-    ap.add_argument("--elem-kernel", type=int, default=int(os.environ.get("JX_ELEM_KERNEL", "3")))
+    ap.add_argument("--elem-kernel", type=int, default=int(os.environ.get("JX_ELEM_KERNEL", "9")))
     ap.add_argument("--ref-nel", type=int, default=12)
     ap.add_argument("--cpu-nel", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
@@ -311,6 +311,13 @@ def main():
         return 0
 
     peak, peak_src = peaks()
+    traffic = None   # dram bytes of one element-kernel launch from the committed ncu --set full capture of this workload
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01g_elem_traffic.json")))
+        if (tr["elem_kernel"], tr["nel"], tr["nop"], tr["pert"]) == (a.elem_kernel, a.nel, a.nop, bool(a.pert)) and not a.visc:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
     elem_ms = phases[1] / a.steps
     elem_bytes = elem_kernel_bytes_per_node(a.nop, a.pert) * N
     achieved = elem_bytes / (elem_ms * 1e-3) / 1e9 if elem_ms > 0 else 0.0
@@ -327,8 +334,8 @@ def main():
                                          zip(("bc", "elem", "dss", "halo", "update", "aux"), phases[:6])},
                    "fused_stage_ms_per_step": ms_f / a.steps,
                    "fused_stage_gdofs": total_dofs / (ms_f / a.steps * 1e-3) / 1e9},
-        "roofline": {"bound": "hbm", "kernel": "k_elem (fused flux + divergence, per element)", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "k_elem_team (fused flux + divergence per element group; variant %d)" % a.elem_kernel, "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": elem_bytes, "launch_ms": elem_ms,
                      "whole_rhs": {"achieved": rhs_gbs, "frac": rhs_gbs / peak, "bytes_per_node": algorithmic_bytes_per_node(a.nop, a.pert)}},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
