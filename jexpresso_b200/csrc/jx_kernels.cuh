@@ -1377,20 +1377,32 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
 #pragma unroll
         for (int r = 0; r < R; ++r) fidn[r] = r * NT + t < C::NNODE ? __ldcs(fi + r * NT + t) : 0;
     }
+    // (the first group's gathers are issued below, once issue_gathers is defined)
     // ---- pieces shared by the roles (inlined into each role's branch so that every role has its own register
     //      allocation: the plane metrics and the zeta metrics never coexist).  All warps take part in the flux
-    //      phase: giving it to the zeta warps alone (with the next group's gathers held in their registers) was
-    //      measured 35 % slower (profiles/r01f) -- the flux arithmetic, not the gather latency, is what counts.
-    auto issue_gathers = [&](int cnt, const int(&fid)[R], double(&qa)[R][NCOMP], bool(&nv)[R]) {
+    //      phase (giving it to the zeta warps alone was measured 35 % slower, profiles/r01f).
+    // q / aux gathers of the NEXT group, staged asynchronously (cp.async, no registers, no scoreboard) in the
+    // flux tiles of the first NST equations, which are dead once their zeta step is done: issued by every warp
+    // at the start of step ISSUE_STEP and consumed by the next group's flux phase, so the gather latency is
+    // covered by the remaining equation steps.  Staged component x of group node n lives at X[x*GB + n]; the
+    // flux phase reads its own node's values before it overwrites position n of every tile.
+    constexpr int NST = (NCOMP + 2) / 3, ISSUE_STEP = NST + 1;
+    static_assert(ISSUE_STEP <= NEQ, "not enough dead flux tiles to stage the gathers");
+    auto issue_gathers = [&](int64_t g, const int(&fid)[R]) {
+        if (g < ngroups) {
+            const int cnt = (int)(a.nelem - g * EPB < EPB ? a.nelem - g * EPB : EPB);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            nv[r] = r * NT + t < cnt * NP;
-            const int64_t node = nv[r] ? fid[r] : 0;
+            for (int r = 0; r < R; ++r) {
+                const int n = r * NT + t;
+                if (n < cnt * NP) {
 #pragma unroll
-            for (int e = 0; e < NQ; ++e) qa[r][e] = nv[r] ? __ldg(a.u + (size_t)e * a.npoin + node) : 1.0;
+                    for (int e = 0; e < NQ; ++e) cp_async8(X + e * GB + n, a.u + (size_t)e * a.npoin + fid[r]);
 #pragma unroll
-            for (int x = 0; x < EQ::NAUX; ++x) qa[r][NQ + x] = nv[r] ? __ldg(a.aux + (size_t)x * a.npoin + node) : 1.0;
+                    for (int x = 0; x < EQ::NAUX; ++x) cp_async8(X + (NQ + x) * GB + n, a.aux + (size_t)x * a.npoin + fid[r]);
+                }
+            }
         }
+        cp_async_commit();
     };
     auto prefetch_next = [&](int64_t gn, int(&fid)[R]) {   // next group: flux-view node ids -> registers, record -> L2
         if (gn < ngroups) {
@@ -1403,16 +1415,19 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
         }
     };
     // flux / source at every node of the group, node-parallel (group node n = slot*NP + l)
-    auto flux_phase = [&](const double(&qa)[R][NCOMP], const bool(&nv)[R]) {
+    // flux / source at every node of the group, node-parallel (group node n = slot*NP + l), from the staged gathers
+    auto flux_phase = [&](int cnt) {
+        cp_async_wait<0>();
+        __syncwarp();
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            if (nv[r]) {
-                const int ad = r * NT + t;
+            const int ad = r * NT + t;
+            if (ad < cnt * NP) {
                 double q[NEQ], ax[EQ::NAUX], f[NEQ], gg[NEQ], h[NEQ];
 #pragma unroll
-                for (int e = 0; e < NEQ; ++e) q[e] = e < NQ ? qa[r][e < NQ ? e : 0] : 1.0;
+                for (int e = 0; e < NEQ; ++e) q[e] = e < NQ ? X[(e < NQ ? e : 0) * GB + ad] : 1.0;
 #pragma unroll
-                for (int x = 0; x < EQ::NAUX; ++x) ax[x] = qa[r][NQ + x];
+                for (int x = 0; x < EQ::NAUX; ++x) ax[x] = X[(NQ + x) * GB + ad];
                 EQ::flux_aux(a.phys, q, ax, f, gg, h);
 #pragma unroll
                 for (int e = 0; e < NEQ; ++e) {
@@ -1435,18 +1450,16 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
         for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
             const int cnt = (int)(a.nelem - g * EPB < EPB ? a.nelem - g * EPB : EPB);
             const double *pl = reinterpret_cast<const double *>(a.rec + (size_t)g * C::GROUP_BYTES);
-            double qa[R][NCOMP];
-            bool nv[R];
-            issue_gathers(cnt, fidn, qa, nv);
             double mxi[NN], met[NN];             // xi_X, eta_X at this warp's nodes of plane k (lane-major streams)
 #pragma unroll
             for (int n = 0; n < NN; ++n) { mxi[n] = __ldcs(pl + (LO + n) * 32 + lane); met[n] = __ldcs(pl + (NC + LO + n) * 32 + lane); }
+            flux_phase(cnt);
             prefetch_next(g + gridDim.x, fidn);
-            flux_phase(qa, nv);
             block_sync();
             const bool live = pact && ps < cnt;
 #pragma unroll 1
             for (int step = 0; step <= NEQ; ++step) {
+                if (step == ISSUE_STEP) issue_gathers(g + gridDim.x, fidn);
                 if (step < NEQ && live) {
                     const double *T = X + (size_t)(step * 3 + pX) * GB + poff;
                     double *Bo = B + (size_t)((step & 1) * 3 + pX) * GB + poff;
@@ -1477,6 +1490,7 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
             }
         }
     };
+    issue_gathers(blockIdx.x, fidn);         // first group: nothing to hide behind
     if (plane_warp) {
         // =============================== PLANE ROLE ===============================
         if constexpr (PW == 1) plane_role(std::integral_constant<int, 0>{}, std::integral_constant<int, NC>{});
@@ -1492,9 +1506,6 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
             const char *rec = a.rec + (size_t)g * C::GROUP_BYTES;
             const double *zs = reinterpret_cast<const double *>(rec + C::Z_OFF);
             const int32_t *zid = reinterpret_cast<const int32_t *>(rec + C::ZID_OFF);
-            double qa[R][NCOMP];
-            bool nv[R];
-            issue_gathers(cnt, fidn, qa, nv);
             double mz[SPW][3][N], wj[SPW][N];
             int ip[SPW][N];
 #pragma unroll
@@ -1510,11 +1521,12 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
                     ip[sl][m] = __ldcs(zid + (s * N + m) * 32 + lane);
                 }
             }
+            flux_phase(cnt);
             prefetch_next(g + gridDim.x, fidn);
-            flux_phase(qa, nv);
             block_sync();
 #pragma unroll 1
             for (int step = 0; step <= NEQ; ++step) {
+                if (step == ISSUE_STEP) issue_gathers(g + gridDim.x, fidn);
                 if (step >= 1) {
                     const int e = step - 1;
 #pragma unroll
