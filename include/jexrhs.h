@@ -61,6 +61,8 @@ typedef struct jx_ctx jx_ctx;
 #define JX_OPT_POW_MODE 2      /* 0 = CUDA pow() (default); 1 = jx_pow (include/jxpow.h), bit-identical
                                   to the oracle's jx_pow */
 #define JX_OPT_ELEM_KERNEL 3   /* element-kernel variant, 0 = default */
+#define JX_OPT_CUDA_GRAPH 4    /* 1: jx_bench_rhs captures one RHS evaluation (kernels + NCCL groups) in a CUDA graph and
+                                  replays it; per-phase timing then uses a separate eager pass */
 
 /* replaces: MPI.Init / get_mpi_comm (src/run.jl:74-88).  nccl_uid: 128-byte ncclUniqueId shared
  * by all ranks (see jx_nccl_unique_id) or NULL when nranks == 1. */

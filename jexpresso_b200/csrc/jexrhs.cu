@@ -129,7 +129,9 @@ struct jx_ctx {
     float last_ms = 0.f;
     bool phase_timing = false;
     std::vector<cudaEvent_t> ph_ev;                  // pairs (start, stop) tagged by ph_tag
+    std::vector<cudaEvent_t> ph_pool;                // recycled events
     std::vector<int> ph_tag;
+    int use_graph = 0;                               // jx_bench_rhs / jx_step replay one captured RHS (JX_OPT_CUDA_GRAPH)
 };
 
 namespace {
@@ -181,8 +183,13 @@ struct PhaseScope {
     PhaseScope(jx_ctx *c_, int tag) : c(c_), on(c_->phase_timing) {
         if (!on) return;
         cudaEvent_t a, b;
-        cudaEventCreate(&a);
-        cudaEventCreate(&b);
+        if (c->ph_pool.size() >= 2) {          // events are recycled between jx_bench_rhs calls
+            a = c->ph_pool.back(); c->ph_pool.pop_back();
+            b = c->ph_pool.back(); c->ph_pool.pop_back();
+        } else {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+        }
         c->ph_ev.push_back(a);
         c->ph_ev.push_back(b);
         c->ph_tag.push_back(tag);
@@ -279,6 +286,7 @@ extern "C" void jx_destroy(jx_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_mesh(c); free_bcs(c); free_halo(c);
     for (auto e : c->ph_ev) cudaEventDestroy(e);
+    for (auto e : c->ph_pool) cudaEventDestroy(e);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -305,6 +313,7 @@ extern "C" int jx_set_option(jx_ctx *c, int key, int64_t value) {
             c->pow_mode = (int)value;
             break;
         case JX_OPT_ELEM_KERNEL: c->elem_variant = (int)value; break;
+        case JX_OPT_CUDA_GRAPH: c->use_graph = value ? 1 : 0; return JX_OK;
         default: return fail(c, JX_EINVAL, "unknown option %d", key);
     }
     if (c->have_problem) {
@@ -692,9 +701,11 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     ea.atomics = atomics ? 1 : 0; ea.lsource = c->lsource; ea.phys = c->phys;
     for (int i = 0; i < 8; ++i) ea.visc[i] = c->visc[i];
     for (int i = 0; i < 64; ++i) ea.dpsi[i] = c->dpsi[i];
-    // atomics mode folds M^-1 into the scatter unless an exchange of un-scaled sums follows
-    const bool fold_minv = atomics && !c->have_halo;
-    if (atomics && !fold_minv) ea.Minv = nullptr;
+    // atomics mode folds M^-1 into the scatter weight.  With an interface exchange the ranks then sum already
+    // scaled partials (M^-1 is the globally assembled value, identical on every copy of a node): one rounding per
+    // contribution instead of one per node, inside the tolerance the unordered mode has anyway, and no extra
+    // pass over du.  The deterministic mode keeps the reference order (exchange, then divide_by_mass_matrix!).
+    const bool fold_minv = atomics;
     ea.aux = nullptr;
     if (ks->launch_aux) {                                                // per-node flux ingredient (+ zero-fill of du)
         PhaseScope ps(c, PH_AUX);
@@ -733,9 +744,11 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
             int rc = assemble(c, du);
             if (rc) return rc;
         }
-        PhaseScope ps(c, PH_UPDATE);
-        k_scale_minv<<<nblk(N * q, 256), 256, 0, s>>>(du, c->Minv, N, q);   // rhs.jl:698-699
-        c->launches++;
+        if (!fold_minv) {
+            PhaseScope ps(c, PH_UPDATE);
+            k_scale_minv<<<nblk(N * q, 256), 256, 0, s>>>(du, c->Minv, N, q);   // rhs.jl:698-699
+            c->launches++;
+        }
     }
     if (upd.kind == 1) {
         PhaseScope ps(c, PH_UPDATE);
@@ -891,24 +904,51 @@ extern "C" int jx_bench_rhs(jx_ctx *c, int n, int fused_stage, float *total_ms, 
     if (!c || n <= 0) return JX_EINVAL;
     if (!c->have_mesh) return fail(c, JX_ESTATE, "jx_bench_rhs before jx_upload_mesh");
     cudaSetDevice(c->device);
-    for (auto e : c->ph_ev) cudaEventDestroy(e);
+    for (auto e : c->ph_ev) c->ph_pool.push_back(e);
     c->ph_ev.clear(); c->ph_tag.clear();
     c->phase_timing = phase_ms != nullptr;
-    CK(cudaStreamSynchronize(c->stream));
-    CK(cudaEventRecord(c->ev0, c->stream));
+    StageUpdate upd;
+    if (fused_stage) {   // a dt = 0 CK2N54 stage: full stage traffic, state unchanged
+        upd.kind = 1; upd.A = CK_A[1]; upd.B = CK_B[1]; upd.dt = 0.0; upd.first = 0;
+    }
     int rc = JX_OK;
-    for (int i = 0; i < n && rc == JX_OK; ++i) {
-        StageUpdate upd;
-        if (fused_stage) {   // a dt = 0 CK2N54 stage: full stage traffic, state unchanged
-            upd.kind = 1; upd.A = CK_A[1]; upd.B = CK_B[1]; upd.dt = 0.0; upd.first = 0;
-        }
+    // CUDA graph path (no per-phase events): one RHS evaluation -- kernels, NCCL send/recv groups, copies -- is
+    // captured once and replayed n times, so the host's enqueue cost (dominant at N > 1: two NCCL groups and six
+    // small kernels per evaluation) leaves the timed region.
+    cudaGraphExec_t gexec = nullptr;
+    if (c->use_graph && !c->phase_timing) {
+        rc = rhs_core(c, c->u, c->du, upd);                 // eager once: lazy allocations happen outside the capture
+        if (rc) return rc;
+        cudaGraph_t graph = nullptr;
+        const int64_t l0 = c->launches;
+        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
         rc = rhs_core(c, c->u, c->du, upd);
+        cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        const int64_t per = c->launches - l0;
+        c->launches = l0;
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail(c, JX_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&gexec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail(c, JX_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaEventRecord(c->ev0, c->stream));
+        for (int i = 0; i < n; ++i) {
+            ce = cudaGraphLaunch(gexec, c->stream);
+            if (ce != cudaSuccess) { cudaGraphExecDestroy(gexec); return fail(c, JX_ECUDA, "cudaGraphLaunch: %s", cudaGetErrorString(ce)); }
+        }
+        c->launches += per * n;
+    } else {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaEventRecord(c->ev0, c->stream));
+        for (int i = 0; i < n && rc == JX_OK; ++i) rc = rhs_core(c, c->u, c->du, upd);
     }
     c->phase_timing = false;
     if (rc) return rc;
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    if (gexec) cudaGraphExecDestroy(gexec);
     if (total_ms) *total_ms = c->last_ms;
     if (phase_ms) {
         for (int i = 0; i < PH_COUNT; ++i) phase_ms[i] = 0.f;

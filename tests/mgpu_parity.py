@@ -1,0 +1,69 @@
+"""Multi-GPU parity check (one rank per GPU, NCCL interface exchange inside libjexrhs), launched as
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/mgpu_parity.py
+Every rank evaluates one rhs! and 3 CK2N54 steps of a small periodic-xy / free-slip-z 3D CompEuler box on its own
+partition; rank r compares its result with the oracle's all-ranks restatement (computed redundantly on the host).
+Deterministic DSS: bit-exact; atomics DSS (bench configuration, team kernel): <= 1e-12 per node, <= 1e-10 L2.
+Not collected by pytest (needs torchrun); the CPU suite covers the same partition / assembler lists over gloo."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from helpers import MU3, PHYS, box3d, euler_case, rel_err_per_node
+    from jexpresso_b200 import capi
+    from jexpresso_b200 import rhs as jrhs
+    from oracle import ref
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for periodic, lvisc, dss, variant in (((True, True, False), True, 0, 0), ((False, False, False), False, 0, 9),
+                                          ((True, True, False), False, 1, 9)):
+        box = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        spec = box3d((6, 4, 3), 4, warp=0.05, periodic=periodic)
+        sems, qns, qes, us = euler_case(spec, world, lpert=False)
+        probs = [ref.RefProblem(s, qe, eq_id=0, lpert=False, lsource=True, lvisc=lvisc, visc_coeff=MU3, phys=PHYS, pow_mode=1)
+                 for s, qe in zip(sems, qes)]
+        caches = ref.setup_assembler([s.mesh.ip2gip for s in sems], [s.mesh.gip2owner for s in sems])
+        run = ref.RefRun(probs, caches)
+        uo = [u.copy() for u in us]
+        duo = [np.zeros_like(u) for u in us]
+        run.rhs(duo, uo, 0.0)
+        inputs = {"SOL_VARS_TYPE": "TOTAL", "lsource": True, "lvisc": lvisc, "mu": MU3, "dt": 0.4, "ode_solver": "CarpenterKennedy2N54"}
+        p = jrhs.params_setup(sems[rank], qes[rank], inputs, device=local, rank=rank, nranks=world, nccl_uid=box[0],
+                              pow_mode=1, dss_mode=dss, elem_kernel=variant)
+        try:
+            u = us[rank].copy()
+            du = np.empty_like(u)
+            jrhs.rhs_bang(du, u, p, 0.0)
+            ug = us[rank].copy()
+            jrhs.time_loop_bang(inputs, p, ug, 3)
+        finally:
+            p.close()
+        us2 = [x.copy() for x in us]
+        ref.time_loop(run, us2, 0.0, inputs["dt"], 3, scheme="CK2N54")
+        pn, l2 = rel_err_per_node(du, duo[rank])
+        pn2, l22 = rel_err_per_node(ug, us2[rank])
+        exact = bool(np.array_equal(du, duo[rank]) and np.array_equal(ug, us2[rank]))
+        good = exact if dss == 0 else (pn <= 1e-12 and l2 <= 1e-10 and pn2 <= 1e-12 and l22 <= 1e-10)
+        ok &= good
+        print(f"[rank {rank}/{world}] periodic={periodic} visc={lvisc} dss={dss} kernel={variant}: rhs pn={pn:.2e} l2={l2:.2e} "
+              f"3 steps pn={pn2:.2e} l2={l22:.2e} bit_exact={exact} -> {'OK' if good else 'FAIL'}", flush=True)
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
