@@ -205,6 +205,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
+    if a.elem_kernel >= 1 and (a.visc or a.nop not in (2, 4)):
+        a.elem_kernel = 0        # the 3D fast paths are inviscid, nop <= 4; everything else runs the generic k_elem_node
     if a.impl == "reference":
         return run_reference(a)
 
