@@ -13,7 +13,7 @@ import re
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libjexrhs.so")
+LIB_PATH = os.environ.get("JX_LIB") or os.path.join(_HERE, "lib", "libjexrhs.so")   # JX_LIB: alternative build (kernel experiments)
 HEADER_PATH = os.path.join(_HERE, "..", "include", "jexrhs.h")
 
 JX_OK, JX_EINVAL, JX_ENODEV, JX_ECUDA, JX_ESTATE, JX_ENCCL, JX_ENOMEM = 0, -1, -2, -3, -4, -5, -6

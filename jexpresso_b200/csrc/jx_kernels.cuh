@@ -1316,6 +1316,12 @@ k_elem_gpencil(const __grid_constant__ ElemArgs a) {
 // ------------------------------------------------------------------------------------------
 // ZW = number of zeta-role warps (1: one warp walks all element slots; EPB: one warp per slot).
 // MODE = 0: rhs_el store (deterministic DSS); 1: RED.ADD of omega*J-weighted values; 2: RED.ADD with M^-1 pre-folded
+#ifndef JX_TEAM_L2PF
+#define JX_TEAM_L2PF 1          // pull the next group's record into L2 one group ahead
+#endif
+#ifndef JX_TEAM_CHUNK
+#define JX_TEAM_CHUNK 5         // plane role: outputs in flight (2 FMA chains each)
+#endif
 template <int NGL, class EQ, int ZW = 1, int PW = 1>
 struct ElemTeamCfg {
     static constexpr int N = NGL, NC = NGL * NGL, NP = NGL * NGL * NGL, NEQ = EQ::NEQ;
@@ -1409,9 +1415,11 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
             const int32_t *fi = fid_of(gn);
 #pragma unroll
             for (int r = 0; r < R; ++r) fid[r] = r * NT + t < C::NNODE ? __ldcs(fi + r * NT + t) : 0;
+#if JX_TEAM_L2PF
             constexpr int CH = 1024;
             for (int off = t * CH; off < C::FID_OFF; off += NT * CH)
                 prefetch_l2_bulk(a.rec + (size_t)gn * C::GROUP_BYTES + off, (C::FID_OFF - off) < CH ? (C::FID_OFF - off) : CH);
+#endif
         }
     };
     // flux / source at every node of the group, node-parallel (group node n = slot*NP + l)
@@ -1446,7 +1454,7 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
     // both read the whole plane, each keeps only its own metric terms -> half the registers, half the step time)
     auto plane_role = [&](auto lo_c, auto hi_c) {
         constexpr int LO = decltype(lo_c)::value, HI = decltype(hi_c)::value, NN = HI - LO;
-        constexpr int CHUNK = 5;                 // outputs in flight: 2*CHUNK independent FMA chains
+        constexpr int CHUNK = JX_TEAM_CHUNK;     // outputs in flight: 2*CHUNK independent FMA chains
         for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
             const int cnt = (int)(a.nelem - g * EPB < EPB ? a.nelem - g * EPB : EPB);
             const double *pl = reinterpret_cast<const double *>(a.rec + (size_t)g * C::GROUP_BYTES);
