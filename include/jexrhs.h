@@ -60,7 +60,12 @@ typedef struct jx_ctx jx_ctx;
                                   order (default); 1 = atomics (red.global.add.f64), M^-1 folded */
 #define JX_OPT_POW_MODE 2      /* 0 = CUDA pow() (default); 1 = jx_pow (include/jxpow.h), bit-identical
                                   to the oracle's jx_pow */
-#define JX_OPT_ELEM_KERNEL 3   /* element-kernel variant, 0 = default */
+#define JX_OPT_ELEM_KERNEL 3   /* element-kernel variant: JX_ELEM_AUTO (default) picks the fastest exact-order kernel that
+                                  exists for the configuration (3D inviscid nop 2/4: the warp-team kernel, else the generic
+                                  one); JX_ELEM_GENERIC forces the generic thread-per-node kernel; 1..9 name a variant
+                                  (DESIGN.md section 4).  All exact-order variants give bit-identical results. */
+#define JX_ELEM_AUTO 0
+#define JX_ELEM_GENERIC (-1)
 #define JX_OPT_CUDA_GRAPH 4    /* 1: jx_bench_rhs captures one RHS evaluation (kernels + NCCL groups) in a CUDA graph and
                                   replays it; per-phase timing then uses a separate eager pass */
 

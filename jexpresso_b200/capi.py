@@ -18,6 +18,7 @@ HEADER_PATH = os.path.join(_HERE, "..", "include", "jexrhs.h")
 
 JX_OK, JX_EINVAL, JX_ENODEV, JX_ECUDA, JX_ESTATE, JX_ENCCL, JX_ENOMEM = 0, -1, -2, -3, -4, -5, -6
 JX_OPT_DSS_MODE, JX_OPT_POW_MODE, JX_OPT_ELEM_KERNEL, JX_OPT_CUDA_GRAPH = 1, 2, 3, 4
+JX_ELEM_AUTO, JX_ELEM_GENERIC = 0, -1
 _ERRNAMES = {-1: "JX_EINVAL", -2: "JX_ENODEV", -3: "JX_ECUDA", -4: "JX_ESTATE", -5: "JX_ENCCL", -6: "JX_ENOMEM"}
 
 

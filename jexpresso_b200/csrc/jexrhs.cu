@@ -221,19 +221,30 @@ void free_halo(jx_ctx *c) {
 
 int select_kernels(jx_ctx *c) {
     const KernelSet *ks = nullptr;
-    if (c->eq_id == JX_EQ_EULER_THETA && c->nsd == 3)
-        ks = lookup_euler_theta_3d(c->ngl, c->lpert, c->pow_mode, c->lvisc, c->elem_variant);
-    else if (c->eq_id == JX_EQ_EULER_THETA && c->nsd == 2)
-        ks = lookup_euler_theta_2d(c->ngl, c->lpert, c->pow_mode, c->lvisc, c->elem_variant);
-    else
-        ks = lookup_other(c->nsd, c->ngl, c->eq_id, c->lvisc, c->elem_variant);
+    auto lookup = [&](int variant) -> const KernelSet * {
+        if (c->eq_id == JX_EQ_EULER_THETA && c->nsd == 3) return lookup_euler_theta_3d(c->ngl, c->lpert, c->pow_mode, c->lvisc, variant);
+        if (c->eq_id == JX_EQ_EULER_THETA && c->nsd == 2) return lookup_euler_theta_2d(c->ngl, c->lpert, c->pow_mode, c->lvisc, variant);
+        return lookup_other(c->nsd, c->ngl, c->eq_id, c->lvisc, variant);
+    };
+    if (c->elem_variant == JX_ELEM_AUTO) {
+        // fastest exact-order kernel that exists for this configuration: the warp-team kernels (bit-identical to the
+        // generic one), else the generic thread-per-node kernel.  Resident records pin the choice to their layout.
+        const int order[] = {9, 8, 0};
+        for (int v : order) {
+            ks = lookup(v);
+            if (ks && (!c->have_mesh || ks->rec_layout == c->rec_layout)) break;
+            ks = nullptr;
+        }
+    } else {
+        ks = lookup(c->elem_variant == JX_ELEM_GENERIC ? 0 : c->elem_variant);
+    }
     if (!ks)
         return fail(c, JX_EINVAL, "no kernel for nsd=%d ngl=%d eq=%d lpert=%d pow=%d lvisc=%d variant=%d", c->nsd, c->ngl,
                     c->eq_id, c->lpert, c->pow_mode, c->lvisc, c->elem_variant);
     if (ks->neq != c->neqs) return fail(c, JX_EINVAL, "equation set %d has %d equations, got neqs=%d", c->eq_id, ks->neq, c->neqs);
     if (c->have_mesh && ks->rec_layout != c->rec_layout)
         return fail(c, JX_ESTATE, "kernel variant %d reads element-record layout %d, the resident records have layout %d: "
-                    "set JX_OPT_ELEM_KERNEL before jx_upload_mesh", c->elem_variant, ks->rec_layout, c->rec_layout);
+                    "set JX_OPT_ELEM_KERNEL before jx_upload_mesh", ks->variant, ks->rec_layout, c->rec_layout);
     CK(ks->prepare());
     c->ks = ks;
     return JX_OK;

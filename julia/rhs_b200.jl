@@ -34,6 +34,12 @@ function b200_setup(params, inputs; device = 0, rank = 0, nranks = 1, uid = C_NU
     PhysConst = params.PhysConst
     phys = Float64[PhysConst.C0, PhysConst.γ, PhysConst.g, PhysConst.Rair, PhysConst.cp, PhysConst.cv,
                    PhysConst.pref, PhysConst.γm1, 0.0, 0.0, 0.0]
+    # engine options (include/jexrhs.h): inputs[:b200_dss] = :gather (deterministic, reference summation order, default)
+    # or :atomics (throughput mode); the element kernel is chosen by the library (JX_ELEM_AUTO) unless
+    # inputs[:b200_elem_kernel] names a variant; the shared jx_pow keeps the equation of state reproducible
+    check(c, ccall((:jx_set_option, LIB), Cint, (Ctx, Cint, Int64), c, 1, get(inputs, :b200_dss, :gather) == :atomics ? 1 : 0))
+    check(c, ccall((:jx_set_option, LIB), Cint, (Ctx, Cint, Int64), c, 2, get(inputs, :b200_pow, 1)))
+    check(c, ccall((:jx_set_option, LIB), Cint, (Ctx, Cint, Int64), c, 3, get(inputs, :b200_elem_kernel, 0)))
     μ = Float64.(params.visc_coeff)                                          # inputs[:μ], params_setup.jl:307-315
     lpert = inputs[:SOL_VARS_TYPE] == PERT() ? 1 : 0
     check(c, ccall((:jx_set_problem, LIB), Cint,

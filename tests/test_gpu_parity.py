@@ -37,15 +37,16 @@ def test_one_rhs_3d_bit_exact(nop, lpert, lvisc):
     spec = box3d(nel, nop, warp=0.05)
     sems, qns, qes, us = euler_case(spec, 1, lpert=lpert)
     dus, ub, _ = _oracle_rhs(sems, qes, us, lpert, lvisc, pow_mode=1)
-    p = jrhs.params_setup(sems[0], qes[0], _inputs(lpert, lvisc, 3), pow_mode=1, dss_mode=0)
-    try:
-        u = us[0].copy()
-        du = np.empty_like(u)
-        jrhs.rhs_bang(du, u, p, 0.0)
-    finally:
-        p.close()
-    assert np.array_equal(u, ub[0]), "boundary-projected state differs from the oracle"
-    assert np.array_equal(du, dus[0]), rel_err_per_node(du, dus[0])
+    for kernel in (-1, 0):     # JX_ELEM_GENERIC (thread per node) and JX_ELEM_AUTO (team kernel where it exists)
+        p = jrhs.params_setup(sems[0], qes[0], _inputs(lpert, lvisc, 3), pow_mode=1, dss_mode=0, elem_kernel=kernel)
+        try:
+            u = us[0].copy()
+            du = np.empty_like(u)
+            jrhs.rhs_bang(du, u, p, 0.0)
+        finally:
+            p.close()
+        assert np.array_equal(u, ub[0]), "boundary-projected state differs from the oracle"
+        assert np.array_equal(du, dus[0]), (kernel, rel_err_per_node(du, dus[0]))
 
 
 @pytest.mark.parametrize("nop", [2, 4, 5, 7])
