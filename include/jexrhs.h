@@ -66,8 +66,8 @@ typedef struct jx_ctx jx_ctx;
                                   (DESIGN.md section 4).  All exact-order variants give bit-identical results. */
 #define JX_ELEM_AUTO 0
 #define JX_ELEM_GENERIC (-1)
-#define JX_OPT_CUDA_GRAPH 4    /* 1: jx_bench_rhs captures one RHS evaluation (kernels + NCCL groups) in a CUDA graph and
-                                  replays it; per-phase timing then uses a separate eager pass */
+#define JX_OPT_CUDA_GRAPH 4    /* 1: jx_bench_rhs captures one RHS evaluation, and jx_step(CK2N54) one whole step (five stages:
+                                  kernels + NCCL groups), in a CUDA graph and replays it; results are identical */
 
 /* replaces: MPI.Init / get_mpi_comm (src/run.jl:74-88).  nccl_uid: 128-byte ncclUniqueId shared
  * by all ranks (see jx_nccl_unique_id) or NULL when nranks == 1. */

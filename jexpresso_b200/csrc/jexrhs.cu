@@ -828,12 +828,44 @@ extern "C" int jx_step(jx_ctx *c, int scheme, double t, double dt, int nsteps) {
     int rc;
     CK(cudaEventRecord(c->ev0, c->stream));
     if (scheme == JX_SCHEME_CK2N54) {
-        for (int n = 0; n < nsteps; ++n)
+        auto one_step = [&]() -> int {
             for (int i = 0; i < 5; ++i) {
                 StageUpdate upd;
                 upd.kind = 1; upd.A = CK_A[i]; upd.B = CK_B[i]; upd.dt = dt; upd.first = (i == 0);
-                if ((rc = rhs_core(c, c->u, c->du, upd))) return rc;
+                const int r = rhs_core(c, c->u, c->du, upd);
+                if (r) return r;
             }
+            return JX_OK;
+        };
+        if (c->use_graph && nsteps > 2) {
+            // the five stages of one step (about 20 launches, plus the NCCL groups at N > 1) are captured once and
+            // replayed: small meshes are launch bound (C2: ~50 us of device work per stage)
+            if ((rc = one_step())) return rc;                   // eager first step: lazy allocations stay outside the capture
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t gexec = nullptr;
+            const int64_t l0 = c->launches;
+            CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+            rc = one_step();
+            cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+            const int64_t per = c->launches - l0;
+            c->launches = l0;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(c, JX_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(c, JX_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+            for (int n = 1; n < nsteps; ++n) {
+                ce = cudaGraphLaunch(gexec, c->stream);
+                if (ce != cudaSuccess) { cudaGraphExecDestroy(gexec); return fail(c, JX_ECUDA, "cudaGraphLaunch: %s", cudaGetErrorString(ce)); }
+            }
+            c->launches += per * (nsteps - 1);
+            ce = cudaStreamSynchronize(c->stream);
+            cudaGraphExecDestroy(gexec);
+            if (ce != cudaSuccess) return fail(c, JX_ECUDA, "jx_step graph replay: %s", cudaGetErrorString(ce));
+        } else {
+            for (int n = 0; n < nsteps; ++n)
+                if ((rc = one_step())) return rc;
+        }
     } else if (scheme == JX_SCHEME_SSPRK33) {
         // OrdinaryDiffEq SSPRK33 perform_step! (FSAL): k = f(uprev) is evaluated on the state itself
         if ((rc = ensure_scratch(c, 1))) return rc;

@@ -240,3 +240,23 @@ def test_shared_reciprocal_division():
         assert ctx.selftest(0, 1 << 24) == 0
     finally:
         ctx.close()
+
+
+def test_step_graph_replay_is_identical():
+    """JX_OPT_CUDA_GRAPH: jx_step replays one captured CK2N54 step; the state after 12 steps must be bit-identical to
+    the eager enqueue (deterministic and atomics... deterministic DSS here), on the small launch-bound C2-like mesh."""
+    from jexpresso_b200 import capi
+    spec = box3d((5, 4, 4), 4, warp=0.05)
+    sems, qns, qes, us = euler_case(spec, 1, lpert=False)
+    inputs = _inputs(False, False, 3)
+    out = []
+    for graph in (0, 1):
+        p = jrhs.params_setup(sems[0], qes[0], inputs, pow_mode=1, dss_mode=0)
+        try:
+            p.ctx.set_option(capi.JX_OPT_CUDA_GRAPH, graph)
+            ug = us[0].copy()
+            jrhs.time_loop_bang(inputs, p, ug, 12)
+            out.append(ug)
+        finally:
+            p.close()
+    assert np.array_equal(out[0], out[1])
