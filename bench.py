@@ -109,14 +109,15 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-def build_problem(nel, nop, lpert, rank, nranks, warp=0.05):
+def build_problem(nel, nop, lpert, rank, nranks, warp=0.05, periodic=False):
     """This rank's SEM bundle + conditioned IC for the weak-scaling box (nel^3 elements per GPU)."""
     from helpers import box3d
     from jexpresso_b200.sem import rtb_initial_state
     from jexpresso_b200.sem.scalable import conformity4ncf_q_rank, sem_setup_rank
     px, py = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[nranks]
     L = 10000.0
-    spec = box3d((nel * px, nel * py, nel), nop, warp=warp, L=(L * px, L * py, L))
+    spec = box3d((nel * px, nel * py, nel), nop, warp=warp, L=(L * px, L * py, L),
+                 periodic=(True, True, False) if periodic else (False, False, False))
     sem = sem_setup_rank(spec, rank, nranks)
     qn, qe = rtb_initial_state(sem.mesh, lpert, seed=1234)
     conformity4ncf_q_rank(sem, qn, 5)                 # params_setup.jl:259-297 IC conditioning
@@ -199,6 +200,9 @@ def main():
     ap.add_argument("--pow-mode", type=int, default=int(os.environ.get("JX_POW_MODE", "1")))
     ap.add_argument("--elem-kernel", type=int, default=int(os.environ.get("JX_ELEM_KERNEL", "9")))
     ap.add_argument("--graph", type=int, default=int(os.environ.get("JX_BENCH_GRAPH", "1")))
+    ap.add_argument("--overlap", type=int, default=int(os.environ.get("JX_OVERLAP", "0")),
+                    help="JX_OPT_OVERLAP: interface groups first, exchange beside the interior launch; value = SMs left to the exchange")
+    ap.add_argument("--periodic", action="store_true", help="periodic x,y box (self-exchange of the twins; small meshes only)")
     ap.add_argument("--ref-nel", type=int, default=12)
     ap.add_argument("--cpu-nel", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
@@ -234,14 +238,15 @@ def main():
         uid = box[0]
 
     t_setup = time.perf_counter()
-    spec, sem, qn, qe = build_problem(a.nel, a.nop, a.pert, rank, world)
+    spec, sem, qn, qe = build_problem(a.nel, a.nop, a.pert, rank, world, periodic=a.periodic)
     neqs = 5
     N = sem.mesh.npoin
     inputs = {"SOL_VARS_TYPE": "PERT" if a.pert else "TOTAL", "lsource": True, "lvisc": a.visc, "mu": MU3, "dt": 0.1,
               "ode_solver": "CarpenterKennedy2N54"}
     params = jrhs.params_setup(sem, qe, inputs, device=local, rank=rank, nranks=world, nccl_uid=uid,
-                               dss_mode=a.dss_mode, pow_mode=a.pow_mode, elem_kernel=a.elem_kernel)
+                               dss_mode=a.dss_mode, pow_mode=a.pow_mode, elem_kernel=a.elem_kernel, overlap=a.overlap)
     ctx = params.ctx
+    split = ctx.split_info()
     u0 = np.ascontiguousarray(qn[:, :neqs].reshape(-1, order="F"))
     ctx.set_state(u0)
     # global unique nodes (weak scaling: shared interface nodes counted once)
@@ -371,6 +376,8 @@ def main():
         "config": {"workload": workload_name(a), "nodes_per_gpu": N, "elements_per_gpu": sem.mesh.nelem, "neqs": neqs,
                    "l2": "inputs (3.9 GB metric records + 1 GB state per GPU) >> 126 MB L2; no flush needed",
                    "dss_mode": a.dss_mode, "pow_mode": a.pow_mode, "elem_kernel": a.elem_kernel, "setup_s": round(setup_s, 1),
+                   "overlap": {"sms_left_to_exchange": a.overlap, "interface_groups": split[0], "interior_groups": split[1]},
+                   "periodic_xy": bool(a.periodic),
                    "phase_ms_per_step": {k: round(v / a.steps, 4) for k, v in
                                          zip(("bc", "elem", "dss", "halo", "update", "aux"), phases[:6])},
                    "timing": "two timed regions of K RHS evaluations each (CUDA events, barrier + sync on both sides, max over ranks): "
@@ -380,7 +387,9 @@ def main():
                    "eager_ms_per_step": ms_eager / a.steps,
                    "fused_stage_ms_per_step": ms_f / a.steps,
                    "fused_stage_gdofs": total_dofs / (ms_f / a.steps * 1e-3) / 1e9},
-        "roofline": {"bound": "hbm", "kernel": "k_elem_team (fused flux + divergence per element group; variant %d)" % a.elem_kernel, "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": ("k_elem_team (fused flux + divergence per element group; variant %d)" % a.elem_kernel) if a.elem_kernel >= 8
+                     else ("k_elem_node (generic fused flux + divergence%s, thread per node)" % (" + AV viscous term" if a.visc else "")) if a.elem_kernel <= 0
+                     else "element kernel variant %d" % a.elem_kernel, "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": elem_bytes, "launch_ms": elem_ms,
                      "whole_rhs": {"achieved": rhs_gbs, "frac": rhs_gbs / peak, "bytes_per_node": algorithmic_bytes_per_node(a.nop, a.pert)}},

@@ -68,6 +68,10 @@ typedef struct jx_ctx jx_ctx;
 #define JX_ELEM_GENERIC (-1)
 #define JX_OPT_CUDA_GRAPH 4    /* 1: jx_bench_rhs captures one RHS evaluation, and jx_step(CK2N54) one whole step (five stages:
                                   kernels + NCCL groups), in a CUDA graph and replays it; results are identical */
+#define JX_OPT_OVERLAP 5       /* n > 0 (atomics DSS + warp-team element kernel + interface lists): the element groups that touch
+                                  a shared node run first and the interface exchange (DSS_global_RHS!, rhs.jl:690) then runs on
+                                  a second stream beside the launch over the interior groups, which leaves n SMs free for it.
+                                  0 (default): one element launch, then the exchange.  May be set at any time */
 
 /* replaces: MPI.Init / get_mpi_comm (src/run.jl:74-88).  nccl_uid: 128-byte ncclUniqueId shared
  * by all ranks (see jx_nccl_unique_id) or NULL when nranks == 1. */
@@ -123,6 +127,10 @@ int jx_last_elapsed_ms(jx_ctx *, float *ms);
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 int64_t jx_launch_count(jx_ctx *);
 int jx_sync(jx_ctx *);
+/* interface-first split in force for the next evaluation (JX_OPT_OVERLAP): numbers of element groups in the launch that
+ * precedes the exchange and in the launch that runs beside it; both 0 when the evaluation uses one launch.  (No reference
+ * counterpart: the reference overlaps nothing, mpi_communications.jl:260-338 blocks in MPI.Waitall.) */
+int jx_split_info(jx_ctx *, int64_t *interface_groups, int64_t *interior_groups);
 
 /* benchmarking helper: `n` device-resident RHS evaluations back to back on the context's stream, timed
  * with CUDA events.  fused_stage != 0 evaluates a full low-storage RK stage (RHS + M^-1 + stage update with

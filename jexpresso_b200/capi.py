@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("JX_LIB") or os.path.join(_HERE, "lib", "libjexrhs.so"
 HEADER_PATH = os.path.join(_HERE, "..", "include", "jexrhs.h")
 
 JX_OK, JX_EINVAL, JX_ENODEV, JX_ECUDA, JX_ESTATE, JX_ENCCL, JX_ENOMEM = 0, -1, -2, -3, -4, -5, -6
-JX_OPT_DSS_MODE, JX_OPT_POW_MODE, JX_OPT_ELEM_KERNEL, JX_OPT_CUDA_GRAPH = 1, 2, 3, 4
+JX_OPT_DSS_MODE, JX_OPT_POW_MODE, JX_OPT_ELEM_KERNEL, JX_OPT_CUDA_GRAPH, JX_OPT_OVERLAP = 1, 2, 3, 4, 5
 JX_ELEM_AUTO, JX_ELEM_GENERIC = 0, -1
 _ERRNAMES = {-1: "JX_EINVAL", -2: "JX_ENODEV", -3: "JX_ECUDA", -4: "JX_ESTATE", -5: "JX_ENCCL", -6: "JX_ENOMEM"}
 
@@ -65,6 +65,7 @@ def lib():
     L.jx_launch_count.argtypes = [vp]
     L.jx_launch_count.restype = i64
     L.jx_sync.argtypes = [vp]
+    L.jx_split_info.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     L.jx_bench_rhs.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
     L.jx_selftest.argtypes = [vp, i32, i64, ctypes.POINTER(i64)]
     _lib = L
@@ -196,6 +197,11 @@ class Context:
 
     def launch_count(self):
         return int(lib().jx_launch_count(self._h))
+
+    def split_info(self):
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        self._ck(lib().jx_split_info(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     def selftest(self, which, n):
         bad = ctypes.c_int64()

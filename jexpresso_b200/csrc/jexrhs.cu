@@ -132,6 +132,16 @@ struct jx_ctx {
     std::vector<cudaEvent_t> ph_pool;                // recycled events
     std::vector<int> ph_tag;
     int use_graph = 0;                               // jx_bench_rhs / jx_step replay one captured RHS (JX_OPT_CUDA_GRAPH)
+
+    // interface-first split (JX_OPT_OVERLAP): groups touching a shared node run first, the exchange then runs on a
+    // second, high-priority stream beside the launch over the interior groups
+    int overlap_sms = 0;                             // 0 = off; n > 0: n SMs kept free of the interior launch
+    bool split_ready = false;
+    int32_t *d_glist = nullptr;                      // [ngroups]: interface groups, then interior groups
+    int n_iface = 0, n_inner = 0;
+    int *d_gctr = nullptr;                           // work counters of the two list-driven launches
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -200,7 +210,14 @@ struct PhaseScope {
     }
 };
 
+void free_split(jx_ctx *c) {
+    dfree(c->d_glist);
+    c->split_ready = false;
+    c->n_iface = c->n_inner = 0;
+}
+
 void free_mesh(jx_ctx *c) {
+    free_split(c);
     dfree(c->u); dfree(c->du); dfree(c->tmp); dfree(c->qe); dfree(c->Minv); dfree(c->coords);
     dfree(c->rhs_el); dfree(c->rhs_el_visc); dfree(c->aux); dfree(c->rec); dfree(c->n2e_ptr); dfree(c->n2e_idx);
     for (auto &p : c->ss) dfree(p);
@@ -212,6 +229,7 @@ void free_bcs(jx_ctx *c) {
     c->nb = 0;
 }
 void free_halo(jx_ctx *c) {
+    free_split(c);
     dfree(c->d_send_i); dfree(c->d_recv_idx); dfree(c->d_recvback_idx); dfree(c->d_sendbuf); dfree(c->d_recvbuf);
     dfree(c->d_add_sel);
     c->send_seg.clear(); c->recv_seg.clear(); c->add_rounds.clear();
@@ -295,7 +313,12 @@ extern "C" void jx_destroy(jx_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     free_mesh(c); free_bcs(c); free_halo(c);
+    dfree(c->d_gctr);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     for (auto e : c->ph_ev) cudaEventDestroy(e);
     for (auto e : c->ph_pool) cudaEventDestroy(e);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
@@ -325,6 +348,11 @@ extern "C" int jx_set_option(jx_ctx *c, int key, int64_t value) {
             break;
         case JX_OPT_ELEM_KERNEL: c->elem_variant = (int)value; break;
         case JX_OPT_CUDA_GRAPH: c->use_graph = value ? 1 : 0; return JX_OK;
+        case JX_OPT_OVERLAP:
+            if (value < 0 || value > 64) return fail(c, JX_EINVAL, "overlap: 0 (off) or the number of SMs kept free (1..64)");
+            c->overlap_sms = (int)value;
+            free_split(c);
+            return JX_OK;
         default: return fail(c, JX_EINVAL, "unknown option %d", key);
     }
     if (c->have_problem) {
@@ -626,10 +654,9 @@ namespace {
 
 // assemble_mpi! (mpi_communications.jl:260-338) on the device: pack -> owners add in ascending
 // sender rank, list order -> owners pack the sums -> send back -> non-owners overwrite.
-int assemble(jx_ctx *c, double *a) {
+int assemble(jx_ctx *c, double *a, cudaStream_t s) {
     const int m = c->neqs;
     const int64_t N = c->npoin;
-    cudaStream_t s = c->stream;
     if (c->nsend > 0) {
         k_pack<<<nblk(c->nsend * m, 256), 256, 0, s>>>(a, N, m, c->d_send_i, c->nsend, c->d_sendbuf);
         c->launches++;
@@ -679,6 +706,59 @@ int assemble(jx_ctx *c, double *a) {
     return JX_OK;
 }
 
+// Interface-first split ("boundary-elements-first kernel ordering to overlap with the interior kernel").
+// Built lazily once mesh, halo lists and options are in place: marks the nodes of the assembler lists, flags every
+// element group whose record names one of them, and lays the group ids out as [interface groups | interior groups].
+// Only the list-driven team kernel (KernelSet::has_dyn) in atomics mode takes part; everything else keeps the
+// single launch followed by the exchange.
+int ensure_split(jx_ctx *c) {
+    if (c->split_ready) return JX_OK;
+    c->split_ready = true;
+    c->n_iface = c->n_inner = 0;
+    if (c->overlap_sms <= 0 || !c->have_halo || !c->have_mesh || !c->ks || !c->ks->has_dyn || c->dss_mode != 1) return JX_OK;
+    if (c->nsend + c->nrecv == 0 || c->nelem == 0) return JX_OK;
+    const KernelSet *ks = c->ks;
+    const int64_t ngroups = (c->nelem + ks->elems_per_block - 1) / ks->elems_per_block;
+    uint8_t *d_mask = nullptr, *d_flag = nullptr;
+    int rc;
+    if ((rc = dalloc(c, &d_mask, (size_t)c->npoin)) || (rc = dalloc(c, &d_flag, (size_t)ngroups))) { dfree(d_mask); return rc; }
+    auto cleanup = [&]() { dfree(d_mask); dfree(d_flag); };
+    cudaStream_t s = c->stream;
+    cudaError_t e = cudaMemsetAsync(d_mask, 0, (size_t)c->npoin, s);
+    if (c->nsend > 0) {
+        k_mark_nodes<<<nblk(c->nsend, 256), 256, 0, s>>>(d_mask, c->d_send_i, c->nsend);
+        k_mark_nodes<<<nblk(c->nsend, 256), 256, 0, s>>>(d_mask, c->d_recvback_idx, c->nsend);
+    }
+    if (c->nrecv > 0) k_mark_nodes<<<nblk(c->nrecv, 256), 256, 0, s>>>(d_mask, c->d_recv_idx, c->nrecv);
+    k_flag_groups<<<nblk(ngroups, 128), 128, 0, s>>>(c->rec, ks->group_bytes, ks->fid_off, ks->elems_per_block * c->np, ngroups, d_mask, d_flag);
+    c->launches += 4;
+    std::vector<uint8_t> flag((size_t)ngroups);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(flag.data(), d_flag, (size_t)ngroups, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cleanup();
+    if (e != cudaSuccess) return fail(c, JX_ECUDA, "interface split: %s", cudaGetErrorString(e));
+    std::vector<int32_t> list;
+    list.reserve((size_t)ngroups);
+    for (int64_t g = 0; g < ngroups; ++g) if (flag[g]) list.push_back((int32_t)g);
+    const int ni = (int)list.size();
+    for (int64_t g = 0; g < ngroups; ++g) if (!flag[g]) list.push_back((int32_t)g);
+    if (ni == 0 || ni == ngroups) return JX_OK;              // nothing to overlap with
+    if ((rc = dalloc(c, &c->d_glist, (size_t)ngroups))) return rc;
+    if (!c->d_gctr && (rc = dalloc(c, &c->d_gctr, 2))) return rc;
+    CK(cudaMemcpy(c->d_glist, list.data(), (size_t)ngroups * 4, cudaMemcpyHostToDevice));
+    if (!c->stream2) {
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, greatest));
+        CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    c->n_iface = ni;
+    c->n_inner = (int)(ngroups - ni);
+    return JX_OK;
+}
+
 struct StageUpdate {
     int kind = 0;          // 0: du = Minv*RHS only; 1: 2N low-storage update of (u, tmp)
     double A = 0, B = 0, dt = 0;
@@ -689,6 +769,10 @@ struct StageUpdate {
 // the Dirichlet kernel; the mass-scaled result lands in `du`; with upd.kind == 1 the low-storage
 // stage update is applied to (u, tmp) as well (fused into the DSS gather when no exchange follows).
 int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
+    if (!c->split_ready) {
+        int rc = ensure_split(c);
+        if (rc) return rc;
+    }
     const KernelSet *ks = c->ks;
     cudaStream_t s = c->stream;
     const int64_t N = c->npoin, E = c->nelem;
@@ -730,6 +814,40 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
         PhaseScope ps(c, PH_DSS);
         CK(cudaMemsetAsync(du, 0, (size_t)N * q * 8, s));
     }
+    ea.glist = nullptr; ea.gctr = nullptr; ea.nlist = 0; ea.reserve_sms = 0;
+    const bool split = atomics && c->have_halo && c->split_ready && c->n_iface > 0 && ks->has_dyn && E > 0;
+    if (split) {
+        // interface groups first; their sums are final once that launch ends, so the exchange (second stream, high
+        // priority) runs beside the launch over the interior groups, which leaves overlap_sms SMs to it
+        const int per_sm = std::max(1, ks->max_blocks_per_sm());
+        const int cap = c->num_sms * per_sm;
+        CK(cudaMemsetAsync(c->d_gctr, 0, 2 * sizeof(int), s));
+        {
+            PhaseScope ps(c, PH_ELEM);
+            ea.glist = c->d_glist; ea.nlist = c->n_iface; ea.gctr = c->d_gctr; ea.reserve_sms = 0;
+            ks->launch_elem(ea, std::min(c->n_iface, cap), s);
+            CK(cudaEventRecord(c->ev_fork, s));
+            ea.glist = c->d_glist + c->n_iface; ea.nlist = c->n_inner; ea.gctr = c->d_gctr + 1;
+            ea.reserve_sms = std::min(c->overlap_sms, c->num_sms / 2);
+            ks->launch_elem(ea, (int)std::min<int64_t>((int64_t)c->n_inner + (int64_t)ea.reserve_sms * per_sm, cap), s);
+            c->launches += 2;
+        }
+        CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        int rc = assemble(c, du, c->stream2);                            // DSS_global_RHS!, rhs.jl:690
+        if (rc) return rc;
+        CK(cudaEventRecord(c->ev_join, c->stream2));
+        {
+            PhaseScope ps(c, PH_HALO);                                   // what is left exposed after the interior launch
+            CK(cudaStreamWaitEvent(s, c->ev_join, 0));
+        }
+        if (upd.kind == 1) {
+            PhaseScope ps(c, PH_UPDATE);
+            k_lsrk_update<<<nblk(N * q, 256), 256, 0, s>>>(u, c->tmp, du, N * q, upd.A, upd.B, upd.dt, upd.first);
+            c->launches++;
+        }
+        CK(cudaGetLastError());
+        return JX_OK;
+    }
     if (E > 0) {
         PhaseScope ps(c, PH_ELEM);
         const int64_t ngroups = (E + ks->elems_per_block - 1) / ks->elems_per_block;
@@ -752,7 +870,7 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     if (c->have_halo) {                                                  // DSS_global_RHS!, rhs.jl:690
         {
             PhaseScope ps(c, PH_HALO);
-            int rc = assemble(c, du);
+            int rc = assemble(c, du, s);
             if (rc) return rc;
         }
         if (!fold_minv) {
@@ -923,6 +1041,20 @@ extern "C" int jx_sync(jx_ctx *c) {
     if (!c) return JX_EINVAL;
     cudaSetDevice(c->device);
     CK(cudaStreamSynchronize(c->stream));
+    return JX_OK;
+}
+
+extern "C" int jx_split_info(jx_ctx *c, int64_t *interface_groups, int64_t *interior_groups) {
+    if (!c || !interface_groups || !interior_groups) return JX_EINVAL;
+    if (!c->have_mesh) return fail(c, JX_ESTATE, "jx_split_info before jx_upload_mesh");
+    cudaSetDevice(c->device);
+    if (!c->split_ready) {
+        int rc = ensure_split(c);
+        if (rc) return rc;
+    }
+    const bool on = c->dss_mode == 1 && c->have_halo && c->n_iface > 0;
+    *interface_groups = on ? c->n_iface : 0;
+    *interior_groups = on ? c->n_inner : 0;
     return JX_OK;
 }
 

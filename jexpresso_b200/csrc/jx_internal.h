@@ -26,6 +26,7 @@ struct KernelSet {
     // rec_layout 4 (group records of k_elem_gpencil): bytes per group, lane columns, id offsets, lane encoders
     int group_bytes = 0, group_nt = 0, zid_off = 0, fid_off = 0, z_off = 0;
     int group_mult[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // [pass][digit]: lane = s*m0 + c0*m1 + c1*m2
+    int has_dyn = 0;                                            // launch_elem honours ElemArgs::glist/gctr (interface-first split)
 };
 
 // each instantiation unit exports one lookup; returns nullptr if it does not hold the combination

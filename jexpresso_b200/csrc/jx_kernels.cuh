@@ -212,6 +212,11 @@ struct ElemArgs {
     const double *coords;  // [nsd][npoin] (only read by functors with NEEDS_XYZ)
     const double *aux;     // [NAUX][npoin] per-node part of the flux (k_node_aux), kernels with EQ::HAS_AUX only
     const int32_t *elist;  // optional element subset (interface / interior split); nullptr = all
+    const int32_t *glist;  // k_elem_team<DYN>: list of element groups this launch processes (interface or interior set)
+    int *gctr;             // k_elem_team<DYN>: work counter (zeroed before the launch); CTAs take list positions from it
+    int nlist;             // length of glist
+    int reserve_sms;       // k_elem_team<DYN>: CTAs landing on SMs with %smid < reserve_sms exit at once (SMs kept free for
+                           // the interface exchange running beside the interior launch)
     int64_t nelem, npoin;  // nelem = number of elements this launch processes
     int atomics;
     int lsource;
@@ -1349,7 +1354,10 @@ struct ElemTeamCfg {
     static constexpr int GROUP_BYTES = round_up(FID_OFF + NNODE * 4, 128);
 };
 
-template <int NGL, class EQ, int ZW, int MODE, int PW>
+// DYN = true: the launch walks a LIST of groups (a.glist) handed out through an atomic counter instead of the static
+// blockIdx stride, and CTAs that land on the first a.reserve_sms SMs leave at once -- the interior launch of the
+// interface-first split keeps those SMs free for the exchange kernels of the second stream.
+template <int NGL, class EQ, int ZW, int MODE, int PW, bool DYN = false>
 static __global__ void __maxnreg__((ElemTeamCfg<NGL, EQ, ZW, PW>::MAXREG))
 k_elem_team(const __grid_constant__ ElemArgs a) {
     using C = ElemTeamCfg<NGL, EQ, ZW, PW>;
@@ -1377,9 +1385,44 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
 #define JX_D(m, i) a.dpsi[(m) + NGL * (i)]
     const int64_t ngroups = (a.nelem + EPB - 1) / EPB;
     auto fid_of = [&](int64_t g) { return reinterpret_cast<const int32_t *>(a.rec + (size_t)g * C::GROUP_BYTES + C::FID_OFF); };
+    // group sequence of this CTA: static stride, or (DYN) list positions taken from the work counter one group ahead;
+    // "no more work" is the group id ngroups, which every consumer below already treats as out of range
+    __shared__ int s_grp[4];
+    int64_t gfirst = blockIdx.x;
+    int gnext = 0;
+    if constexpr (DYN) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if ((int)smid < a.reserve_sms) return;
+        if (t == 0) {
+            const int p0 = atomicAdd(a.gctr, 1), p1 = atomicAdd(a.gctr, 1);
+            s_grp[0] = p0 < a.nlist ? a.glist[p0] : (int)ngroups;
+            s_grp[1] = p1 < a.nlist ? a.glist[p1] : (int)ngroups;
+        }
+        __syncthreads();
+        gfirst = s_grp[0];
+        gnext = s_grp[1];
+    }
+    auto next_of = [&](int64_t g) -> int64_t {
+        if constexpr (DYN) return gnext;
+        else return g + gridDim.x;
+    };
+    auto fetch_ahead = [&]() {      // DYN: thread 0, once per group, between two block barriers of the step loop
+        if constexpr (DYN) {
+            const int p = atomicAdd(a.gctr, 1);
+            s_grp[2] = p < a.nlist ? a.glist[p] : (int)ngroups;
+        }
+    };
+    auto advance = [&](int64_t g) -> int64_t {   // after the last block barrier of a group
+        if constexpr (DYN) {
+            const int64_t r = gnext;
+            gnext = s_grp[2];
+            return r;
+        } else return g + gridDim.x;
+    };
     int fidn[R];
-    if ((int64_t)blockIdx.x < ngroups) {
-        const int32_t *fi = fid_of(blockIdx.x);
+    if (gfirst < ngroups) {
+        const int32_t *fi = fid_of(gfirst);
 #pragma unroll
         for (int r = 0; r < R; ++r) fidn[r] = r * NT + t < C::NNODE ? __ldcs(fi + r * NT + t) : 0;
     }
@@ -1455,19 +1498,22 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
     auto plane_role = [&](auto lo_c, auto hi_c) {
         constexpr int LO = decltype(lo_c)::value, HI = decltype(hi_c)::value, NN = HI - LO;
         constexpr int CHUNK = JX_TEAM_CHUNK;     // outputs in flight: 2*CHUNK independent FMA chains
-        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        for (int64_t g = gfirst; g < ngroups; g = advance(g)) {
             const int cnt = (int)(a.nelem - g * EPB < EPB ? a.nelem - g * EPB : EPB);
             const double *pl = reinterpret_cast<const double *>(a.rec + (size_t)g * C::GROUP_BYTES);
             double mxi[NN], met[NN];             // xi_X, eta_X at this warp's nodes of plane k (lane-major streams)
 #pragma unroll
             for (int n = 0; n < NN; ++n) { mxi[n] = __ldcs(pl + (LO + n) * 32 + lane); met[n] = __ldcs(pl + (NC + LO + n) * 32 + lane); }
             flux_phase(cnt);
-            prefetch_next(g + gridDim.x, fidn);
+            prefetch_next(next_of(g), fidn);
             block_sync();
             const bool live = pact && ps < cnt;
 #pragma unroll 1
             for (int step = 0; step <= NEQ; ++step) {
-                if (step == ISSUE_STEP) issue_gathers(g + gridDim.x, fidn);
+                if (step == ISSUE_STEP) issue_gathers(next_of(g), fidn);
+                if constexpr (DYN && LO == 0) {
+                    if (step == 1 && t == 0) fetch_ahead();
+                }
                 if (step < NEQ && live) {
                     const double *T = X + (size_t)(step * 3 + pX) * GB + poff;
                     double *Bo = B + (size_t)((step & 1) * 3 + pX) * GB + poff;
@@ -1498,7 +1544,7 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
             }
         }
     };
-    issue_gathers(blockIdx.x, fidn);         // first group: nothing to hide behind
+    issue_gathers(gfirst, fidn);             // first group: nothing to hide behind
     if (plane_warp) {
         // =============================== PLANE ROLE ===============================
         if constexpr (PW == 1) plane_role(std::integral_constant<int, 0>{}, std::integral_constant<int, NC>{});
@@ -1508,7 +1554,7 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
         }
     } else {
         // =============================== ZETA ROLE ===============================
-        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        for (int64_t g = gfirst; g < ngroups; g = advance(g)) {
             const int64_t e0 = g * EPB;
             const int cnt = (int)(a.nelem - e0 < EPB ? a.nelem - e0 : EPB);
             const char *rec = a.rec + (size_t)g * C::GROUP_BYTES;
@@ -1530,11 +1576,11 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
                 }
             }
             flux_phase(cnt);
-            prefetch_next(g + gridDim.x, fidn);
+            prefetch_next(next_of(g), fidn);
             block_sync();
 #pragma unroll 1
             for (int step = 0; step <= NEQ; ++step) {
-                if (step == ISSUE_STEP) issue_gathers(g + gridDim.x, fidn);
+                if (step == ISSUE_STEP) issue_gathers(next_of(g), fidn);
                 if (step >= 1) {
                     const int e = step - 1;
 #pragma unroll
@@ -1721,6 +1767,21 @@ static __global__ void k_lincomb(LinArgs a) {
 // interface / periodic assembly (assemble_mpi!, mpi_communications.jl:260-338)
 // buffers are node-major interleaved: buf[i*m + j] = a[idx[i], j]
 // ------------------------------------------------------------------------------------------
+// interface-first split: nodes named by the assembler lists, then the element groups whose records name one of them
+static __global__ void k_mark_nodes(uint8_t *mask, const int64_t *idx, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mask[idx[i]] = 1;
+}
+static __global__ void k_flag_groups(const char *rec, int group_bytes, int fid_off, int nnode, int64_t ngroups, const uint8_t *mask,
+                                     uint8_t *flag) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    const int32_t *fid = reinterpret_cast<const int32_t *>(rec + (size_t)g * group_bytes + fid_off);
+    uint8_t f = 0;
+    for (int n = 0; n < nnode; ++n) f |= mask[fid[n]];
+    flag[g] = f;
+}
+
 static __global__ void k_pack(const double *a, int64_t npoin, int m, const int64_t *idx, int64_t len, double *buf) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= len * m) return;

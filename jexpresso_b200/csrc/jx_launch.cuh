@@ -195,6 +195,7 @@ struct TeamKernel {
         cudaError_t e = cudaFuncSetAttribute(k_elem_team<NGL, EQ, ZW, 0, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_team<NGL, EQ, ZW, 1, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_team<NGL, EQ, ZW, 2, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_team<NGL, EQ, ZW, 2, PW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
         return e;
     }
     static int max_blocks() {
@@ -203,7 +204,9 @@ struct TeamKernel {
         return nb;
     }
     static void launch(const ElemArgs &a, int grid, cudaStream_t s) {
-        if (!a.atomics) k_elem_team<NGL, EQ, ZW, 0, PW><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+        if (a.gctr != nullptr) {   // interface-first split: list-driven launch (atomics DSS with folded M^-1 only)
+            if (a.atomics && a.Minv != nullptr) k_elem_team<NGL, EQ, ZW, 2, PW, true><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+        } else if (!a.atomics) k_elem_team<NGL, EQ, ZW, 0, PW><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
         else if (a.Minv == nullptr) k_elem_team<NGL, EQ, ZW, 1, PW><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
         else k_elem_team<NGL, EQ, ZW, 2, PW><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
     }
@@ -227,6 +230,7 @@ KernelSet make_team_set(int eq_id, int lpert, int jxpow, int variant) {
     ks.launch_gather = &launch_gather_t<EQ::NEQ>;
     ks.launch_aux = &launch_aux_t<EQ>;
     ks.group_bytes = C::GROUP_BYTES; ks.group_nt = 32; ks.zid_off = C::ZID_OFF; ks.fid_off = C::FID_OFF; ks.z_off = C::Z_OFF;
+    ks.has_dyn = 1;
     return ks;
 }
 

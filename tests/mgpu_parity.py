@@ -3,6 +3,8 @@
 Every rank evaluates one rhs! and 3 CK2N54 steps of a small periodic-xy / free-slip-z 3D CompEuler box on its own
 partition; rank r compares its result with the oracle's all-ranks restatement (computed redundantly on the host).
 Deterministic DSS: bit-exact; atomics DSS (bench configuration, team kernel): <= 1e-12 per node, <= 1e-10 L2.
+The last case runs the interface-first split (JX_OPT_OVERLAP: exchange on a second stream beside the interior launch,
+CK2N54 steps replayed as a CUDA graph).  JX_MGPU_CASES="3" (comma separated indices) selects cases.
 Not collected by pytest (needs torchrun); the CPU suite covers the same partition / assembler lists over gloo."""
 import os
 import sys
@@ -26,11 +28,16 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for periodic, lvisc, dss, variant in (((True, True, False), True, 0, 0), ((False, False, False), False, 0, 9),
-                                          ((True, True, False), False, 1, 9)):
+    cases = (((True, True, False), True, 0, 0, (6, 4, 3), 0), ((False, False, False), False, 0, 9, (6, 4, 3), 0),
+             ((True, True, False), False, 1, 9, (6, 4, 3), 0), ((False, False, False), False, 1, 9, (12, 12, 3), 2))
+    pick = os.environ.get("JX_MGPU_CASES")
+    pick = {int(x) for x in pick.split(",")} if pick else set(range(len(cases)))
+    for ci, (periodic, lvisc, dss, variant, nel, overlap) in enumerate(cases):
+        if ci not in pick:
+            continue
         box = [capi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        spec = box3d((6, 4, 3), 4, warp=0.05, periodic=periodic)
+        spec = box3d(nel, 4, warp=0.05, periodic=periodic)
         sems, qns, qes, us = euler_case(spec, world, lpert=False)
         probs = [ref.RefProblem(s, qe, eq_id=0, lpert=False, lsource=True, lvisc=lvisc, visc_coeff=MU3, phys=PHYS, pow_mode=1)
                  for s, qe in zip(sems, qes)]
@@ -41,7 +48,10 @@ def main():
         run.rhs(duo, uo, 0.0)
         inputs = {"SOL_VARS_TYPE": "TOTAL", "lsource": True, "lvisc": lvisc, "mu": MU3, "dt": 0.4, "ode_solver": "CarpenterKennedy2N54"}
         p = jrhs.params_setup(sems[rank], qes[rank], inputs, device=local, rank=rank, nranks=world, nccl_uid=box[0],
-                              pow_mode=1, dss_mode=dss, elem_kernel=variant)
+                              pow_mode=1, dss_mode=dss, elem_kernel=variant, overlap=overlap)
+        split = p.ctx.split_info()
+        if overlap:
+            p.ctx.set_option(capi.JX_OPT_CUDA_GRAPH, 1)
         try:
             u = us[rank].copy()
             du = np.empty_like(u)
@@ -56,8 +66,10 @@ def main():
         pn2, l22 = rel_err_per_node(ug, us2[rank])
         exact = bool(np.array_equal(du, duo[rank]) and np.array_equal(ug, us2[rank]))
         good = exact if dss == 0 else (pn <= 1e-12 and l2 <= 1e-10 and pn2 <= 1e-12 and l22 <= 1e-10)
+        if overlap:
+            good = good and split[0] > 0 and split[1] > 0
         ok &= good
-        print(f"[rank {rank}/{world}] periodic={periodic} visc={lvisc} dss={dss} kernel={variant}: rhs pn={pn:.2e} l2={l2:.2e} "
+        print(f"[rank {rank}/{world}] periodic={periodic} visc={lvisc} dss={dss} kernel={variant} overlap={overlap} split={split}: rhs pn={pn:.2e} l2={l2:.2e} "
               f"3 steps pn={pn2:.2e} l2={l22:.2e} bit_exact={exact} -> {'OK' if good else 'FAIL'}", flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
