@@ -200,8 +200,9 @@ def main():
     ap.add_argument("--pow-mode", type=int, default=int(os.environ.get("JX_POW_MODE", "1")))
     ap.add_argument("--elem-kernel", type=int, default=int(os.environ.get("JX_ELEM_KERNEL", "9")))
     ap.add_argument("--graph", type=int, default=int(os.environ.get("JX_BENCH_GRAPH", "1")))
-    ap.add_argument("--overlap", type=int, default=int(os.environ.get("JX_OVERLAP", "0")),
-                    help="JX_OPT_OVERLAP: interface groups first, exchange beside the interior launch; value = SMs left to the exchange")
+    ap.add_argument("--overlap", type=int, default=int(os.environ.get("JX_OVERLAP", "-1")),
+                    help="JX_OPT_OVERLAP: interface groups first, exchange beside the interior launch; value = SMs left to the "
+                         "exchange (0 = off; -1 = auto: 4 at N > 1, where there is an exchange to hide)")
     ap.add_argument("--periodic", action="store_true", help="periodic x,y box (self-exchange of the twins; small meshes only)")
     ap.add_argument("--ref-nel", type=int, default=12)
     ap.add_argument("--cpu-nel", type=int, default=16)
@@ -213,6 +214,13 @@ def main():
         a.elem_kernel = 0        # the 3D fast paths are inviscid, nop <= 4; everything else runs the generic k_elem_node
     if a.impl == "reference":
         return run_reference(a)
+    if a.overlap < 0:
+        a.overlap = 4 if int(os.environ.get("WORLD_SIZE", "1")) > 1 else 0
+    if a.overlap > 0:
+        # the exchange's NCCL send/recv kernels must fit on the SMs the interior launch leaves free (one CTA per channel,
+        # one CTA per SM): cap the channel count before any communicator exists
+        for k in ("NCCL_MAX_CTAS", "NCCL_MAX_NCHANNELS", "NCCL_MAX_P2P_NCHANNELS"):
+            os.environ.setdefault(k, str(a.overlap))
 
     import torch
     import torch.distributed as dist

@@ -40,6 +40,10 @@ function b200_setup(params, inputs; device = 0, rank = 0, nranks = 1, uid = C_NU
     check(c, ccall((:jx_set_option, LIB), Cint, (Ctx, Cint, Int64), c, 1, get(inputs, :b200_dss, :gather) == :atomics ? 1 : 0))
     check(c, ccall((:jx_set_option, LIB), Cint, (Ctx, Cint, Int64), c, 2, get(inputs, :b200_pow, 1)))
     check(c, ccall((:jx_set_option, LIB), Cint, (Ctx, Cint, Int64), c, 3, get(inputs, :b200_elem_kernel, 0)))
+    # inputs[:b200_overlap] = n > 0 (atomics mode, several ranks): interface elements first, the NCCL exchange beside the
+    # interior launch with n SMs left to it; set ENV["NCCL_MAX_CTAS"] = ENV["NCCL_MAX_P2P_NCHANNELS"] = string(n) before
+    # jx_init so that the send/recv kernels fit on those SMs (JX_OPT_OVERLAP)
+    check(c, ccall((:jx_set_option, LIB), Cint, (Ctx, Cint, Int64), c, 5, get(inputs, :b200_overlap, 0)))
     μ = Float64.(params.visc_coeff)                                          # inputs[:μ], params_setup.jl:307-315
     lpert = inputs[:SOL_VARS_TYPE] == PERT() ? 1 : 0
     check(c, ccall((:jx_set_problem, LIB), Cint,
