@@ -23,7 +23,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-__all__ = ["find_gip_owner_all", "restructure4periodicity_all", "AssemblerLists", "setup_assembler_all"]
+__all__ = ["interface_element_groups", "find_gip_owner_all", "restructure4periodicity_all", "AssemblerLists", "setup_assembler_all"]
 
 
 def find_gip_owner_all(ip2gip_list):
@@ -170,6 +170,26 @@ class AssemblerLists:
 
     def is_trivial(self):
         return not self.active_send_ranks and not self.active_recv_ranks
+
+
+def interface_element_groups(connijk, asm, epb):
+    """Host restatement of libjexrhs' interface-first split (jexrhs.cu: ensure_split): ids of the groups of ``epb``
+    consecutive elements that name a node of the assembler lists, and of the remaining (interior) groups.  Used by the
+    tests to check ``jx_split_info``; the library builds the same lists on the device from its element records."""
+    nelem = connijk.shape[0]
+    npoin = int(connijk.max())
+    mask = np.zeros(npoin + 1, bool)
+    for lists in (asm.send_i, asm.recv_idx, asm.recvback_idx):
+        for v in lists:
+            mask[np.asarray(v, np.int64)] = True
+    touch = mask[connijk.reshape(nelem, -1)].any(axis=1)
+    ngroups = (nelem + epb - 1) // epb
+    pad = np.zeros(ngroups * epb, bool)
+    pad[:nelem] = touch
+    if nelem % epb and mask[1]:
+        pad[nelem:] = True            # empty slots of the last record hold node id 1 (0-based 0)
+    flag = pad.reshape(ngroups, epb).any(axis=1)
+    return np.nonzero(flag)[0], np.nonzero(~flag)[0]
 
 
 class _CyclingReverseDict:

@@ -196,7 +196,9 @@ def test_interface_first_split_overlap_3d(lpert):
         try:
             ni, nn = p.ctx.split_info()
             if overlap:
-                assert ni > 0 and nn > 0 and ni + nn == (sems[0].mesh.nelem + 1) // 2, (ni, nn)
+                from jexpresso_b200.sem.partition import interface_element_groups
+                gi, gn = interface_element_groups(sems[0].mesh.connijk, sems[0].asm, 2)
+                assert len(gi) > 0 and len(gn) > 0 and (ni, nn) == (len(gi), len(gn)), (ni, nn, len(gi), len(gn))
             else:
                 assert (ni, nn) == (0, 0)
             u = us[0].copy()

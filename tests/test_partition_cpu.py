@@ -82,3 +82,27 @@ def test_oracle_partitioned_rhs_matches_single_rank():
     # derivative operators amplify that; 1e-10 of the field scale is summation-order accuracy here
     scale = np.abs(out[1]).max(axis=0)
     assert np.all(np.abs(out[4] - out[1]) <= 1e-10 * scale)
+
+
+def test_interface_element_groups_cover_every_shared_node():
+    """Host restatement of the interface-first split (JX_OPT_OVERLAP): no interior group may touch a node of the
+    assembler lists, every group is in exactly one set, and a 2-rank split of a box has both kinds."""
+    from helpers import box3d
+    from jexpresso_b200.sem import sem_setup
+    from jexpresso_b200.sem.partition import interface_element_groups
+    for nranks, periodic in ((2, (False, False, False)), (1, (True, True, False)), (4, (True, False, False))):
+        sems = sem_setup(box3d((16, 12, 3) if nranks > 1 else (8, 8, 3), 2, periodic=periodic), nranks)
+        for s in sems:
+            for epb in (1, 2, 3):
+                gi, gn = interface_element_groups(s.mesh.connijk, s.asm, epb)
+                ngroups = (s.mesh.nelem + epb - 1) // epb
+                assert sorted(list(gi) + list(gn)) == list(range(ngroups))
+                assert len(gi) > 0 and len(gn) > 0
+                shared = set()
+                for lists in (s.asm.send_i, s.asm.recv_idx, s.asm.recvback_idx):
+                    for v in lists:
+                        shared.update(int(x) for x in v)
+                conn = s.mesh.connijk.reshape(s.mesh.nelem, -1)
+                for g in gn:
+                    els = range(g * epb, min((g + 1) * epb, s.mesh.nelem))
+                    assert not (set(int(x) for e in els for x in conn[e]) & shared)
