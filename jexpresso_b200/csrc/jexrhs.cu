@@ -355,6 +355,7 @@ extern "C" int jx_set_option(jx_ctx *c, int key, int64_t value) {
             return JX_OK;
         default: return fail(c, JX_EINVAL, "unknown option %d", key);
     }
+    free_split(c);   // the split depends on the DSS mode and on the kernel's record layout: rebuilt at the next evaluation
     if (c->have_problem) {
         const int rc = select_kernels(c);
         if (rc) { c->dss_mode = old_dss; c->pow_mode = old_pow; c->elem_variant = old_var; }   // refused: keep the working set
