@@ -181,6 +181,18 @@ def build_oracle_only():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
 
 
+def resolve_overlap(overlap, world, env):
+    """--overlap -1 (auto): interface-first split with 4 SMs left to the exchange when there is one (N > 1), else off.
+    When the split is on, the exchange's NCCL send/recv kernels must fit on those SMs (one CTA per channel, one CTA
+    per SM), so the channel count is capped in ``env`` before any communicator exists."""
+    if overlap < 0:
+        overlap = 4 if world > 1 else 0
+    if overlap > 0:
+        for k in ("NCCL_MAX_CTAS", "NCCL_MAX_NCHANNELS", "NCCL_MAX_P2P_NCHANNELS"):
+            env.setdefault(k, str(overlap))
+    return overlap
+
+
 def workload_name(a):
     return (f"CompEuler theta 3D TOTAL {'AV mu=125' if a.visc else 'inviscid'} + gravity source, nop={a.nop}, "
             f"{a.nel}^3 elements per GPU (synthetic weak-scaling mesh, BASELINE configs[4])")
@@ -214,13 +226,7 @@ def main():
         a.elem_kernel = 0        # the 3D fast paths are inviscid, nop <= 4; everything else runs the generic k_elem_node
     if a.impl == "reference":
         return run_reference(a)
-    if a.overlap < 0:
-        a.overlap = 4 if int(os.environ.get("WORLD_SIZE", "1")) > 1 else 0
-    if a.overlap > 0:
-        # the exchange's NCCL send/recv kernels must fit on the SMs the interior launch leaves free (one CTA per channel,
-        # one CTA per SM): cap the channel count before any communicator exists
-        for k in ("NCCL_MAX_CTAS", "NCCL_MAX_NCHANNELS", "NCCL_MAX_P2P_NCHANNELS"):
-            os.environ.setdefault(k, str(a.overlap))
+    a.overlap = resolve_overlap(a.overlap, int(os.environ.get("WORLD_SIZE", "1")), os.environ)
 
     import torch
     import torch.distributed as dist

@@ -26,3 +26,17 @@ def test_algorithmic_bytes_model():
     assert abs(bench.algorithmic_bytes_per_node(4, True) - 307.875) < 1e-9
     assert abs(bench.algorithmic_bytes_per_node(7, False) - (88 + (8 / 7) ** 3 * 88)) < 1e-9
     assert abs(bench.elem_kernel_bytes_per_node(4, False) - (40 + 1.953125 * 88)) < 1e-9
+
+
+def test_overlap_default_and_nccl_channel_cap():
+    """bench.py turns the interface-first split on only where there is an exchange to hide (N > 1) and caps NCCL's
+    channel count to the SMs the interior launch leaves free -- without overriding a cap the user has set."""
+    sys.path.insert(0, ROOT)
+    import bench
+    env = {}
+    assert bench.resolve_overlap(-1, 1, env) == 0 and env == {}
+    assert bench.resolve_overlap(-1, 8, env) == 4
+    assert env == {"NCCL_MAX_CTAS": "4", "NCCL_MAX_NCHANNELS": "4", "NCCL_MAX_P2P_NCHANNELS": "4"}
+    env = {"NCCL_MAX_CTAS": "8"}
+    assert bench.resolve_overlap(2, 2, env) == 2 and env["NCCL_MAX_CTAS"] == "8" and env["NCCL_MAX_P2P_NCHANNELS"] == "2"
+    assert bench.resolve_overlap(0, 8, {}) == 0
