@@ -95,6 +95,13 @@ int jx_set_problem(jx_ctx *, int nsd, int ngl, int neqs, int64_t nelem, int64_t 
 int jx_upload_mesh(jx_ctx *, const int64_t *connijk, const double *coords, const double *const *metrics, int nmetrics,
                    const double *dpsi, const double *omega, const double *Minv, const double *qe);
 
+/* replaces: build_metric_terms! (src/kernel/mesh/metric_terms.jl:332-474 3D, :197-257 2D) + jx_upload_mesh: the same upload
+ * with the metric terms dξdx..dζdz, Je built on the device from connijk and coords (required here) -- each coordinate
+ * differentiated along the LGL lines in ascending node order, cofactors and determinant with the reference's association --
+ * so the 10 (5) element-sized host arrays need not exist.  Results are bit-identical to the host arrays of the oracle. */
+int jx_upload_mesh_coords(jx_ctx *, const int64_t *connijk, const double *coords, const double *dpsi, const double *omega,
+                          const double *Minv, const double *qe);
+
 /* replaces: params.mesh.poin_in_bdy_face / poin_in_bdy_edge, params.metrics.nx/ny/nz, bdy_face_type
  * (tags mapped to JX_BC_* kinds by the host).  3D arrays are [nfaces, ngl, ngl], 2D [nedges, ngl]. */
 int jx_upload_bcs(jx_ctx *, int64_t nfaces, const int64_t *poin_in_bdy_face, const double *nx, const double *ny,

@@ -54,6 +54,7 @@ def lib():
     L.jx_set_option.argtypes = [vp, i32, i64]
     L.jx_set_problem.argtypes = [vp, i32, i32, i32, i64, i64, i32, i32, i32, i32, vp, vp, i32]
     L.jx_upload_mesh.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp]
+    L.jx_upload_mesh_coords.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.jx_upload_bcs.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.jx_upload_halo.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.jx_set_state.argtypes = [vp, vp]
@@ -141,6 +142,12 @@ class Context:
         c, x, d, o, mi = i64(connijk), f64(coords), f64(dpsi), f64(omega), f64(Minv)
         q = f64(qe) if qe is not None else None
         self._ck(lib().jx_upload_mesh(self._h, _ptr(c), _ptr(x), arr, len(mets), _ptr(d), _ptr(o), _ptr(mi), _ptr(q)))
+
+    def upload_mesh_coords(self, connijk, coords, dpsi, omega, Minv, qe):
+        """jx_upload_mesh with the metric terms built on the device from the coordinates."""
+        c, x, d, o, mi = i64(connijk), f64(coords), f64(dpsi), f64(omega), f64(Minv)
+        q = f64(qe) if qe is not None else None
+        self._ck(lib().jx_upload_mesh_coords(self._h, _ptr(c), _ptr(x), _ptr(d), _ptr(o), _ptr(mi), _ptr(q)))
 
     def upload_bcs(self, poin_in_bdy_face, nx, ny, nz, kinds):
         p = i64(poin_in_bdy_face)

@@ -389,12 +389,11 @@ extern "C" int jx_set_problem(jx_ctx *c, int nsd, int ngl, int neqs, int64_t nel
 // ------------------------------------------------------------------------------------------
 // uploads
 // ------------------------------------------------------------------------------------------
-extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *coords, const double *const *metrics,
-                              int nmetrics, const double *dpsi, const double *omega, const double *Minv, const double *qe) {
-    if (!c) return JX_EINVAL;
-    if (!c->have_problem) return fail(c, JX_ESTATE, "jx_upload_mesh before jx_set_problem");
-    if (!connijk || !metrics || !dpsi || !omega || !Minv) return fail(c, JX_EINVAL, "jx_upload_mesh: null array");
-    if (nmetrics != c->nmet) return fail(c, JX_EINVAL, "expected %d metric arrays, got %d", c->nmet, nmetrics);
+namespace {
+
+// metrics == nullptr: the metric arrays are built on the device from coords (k_build_metric) instead of uploaded
+int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, const double *const *metrics,
+                     const double *dpsi, const double *omega, const double *Minv, const double *qe) {
     cudaSetDevice(c->device);
     free_mesh(c);
     const int64_t E = c->nelem, N = c->npoin;
@@ -419,13 +418,14 @@ extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *c
     for (int i = 0; i < c->ngl * c->ngl; ++i) c->dpsi[i] = dpsi[i];
 
     // staging buffer reused for every element-sized host array
-    double *d_stage = nullptr, *d_omega = nullptr;
+    double *d_stage = nullptr, *d_omega = nullptr, *d_dpsi = nullptr;
     int64_t *d_conn = nullptr;
     int32_t *d_cnt = nullptr;
     if ((rc = dalloc(c, &d_stage, (size_t)std::max<int64_t>(total, N * c->nsd))) || (rc = dalloc(c, &d_omega, (size_t)c->ngl)) ||
-        (rc = dalloc(c, &d_conn, (size_t)total)) || (rc = dalloc(c, &d_cnt, (size_t)N)))
+        (rc = dalloc(c, &d_dpsi, (size_t)c->ngl * c->ngl)) || (rc = dalloc(c, &d_conn, (size_t)total)) ||
+        (rc = dalloc(c, &d_cnt, (size_t)N)))
         return rc;
-    auto cleanup = [&]() { dfree(d_stage); dfree(d_omega); dfree(d_conn); dfree(d_cnt); };
+    auto cleanup = [&]() { dfree(d_stage); dfree(d_omega); dfree(d_dpsi); dfree(d_conn); dfree(d_cnt); };
 #define CKC(call)                                                                                    \
     do {                                                                                             \
         cudaError_t e_ = (call);                                                                     \
@@ -436,6 +436,26 @@ extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *c
     } while (0)
     CKC(cudaMemcpyAsync(d_omega, omega, (size_t)c->ngl * 8, cudaMemcpyHostToDevice, c->stream));
     CKC(cudaMemcpyAsync(d_conn, connijk, (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
+    CKC(cudaMemcpyAsync(d_dpsi, dpsi, (size_t)c->ngl * c->ngl * 8, cudaMemcpyHostToDevice, c->stream));
+    // coords: Julia [nsd, N] -> device [nsd][N]
+    if (coords && N > 0) {
+        std::vector<double> soa((size_t)N * c->nsd);
+        for (int d = 0; d < c->nsd; ++d)
+            for (int64_t ip = 0; ip < N; ++ip) soa[(size_t)d * N + ip] = coords[(size_t)ip * c->nsd + d];
+        CKC(cudaMemcpy(c->coords, soa.data(), soa.size() * 8, cudaMemcpyHostToDevice));
+    } else {
+        CKC(cudaMemsetAsync(c->coords, 0, (size_t)std::max<int64_t>(1, N * c->nsd) * 8, c->stream));
+    }
+    // metric array m in the reference's layout -> d_stage: uploaded, or built from the coordinates on the device
+    auto stage_metric = [&](int m) -> cudaError_t {
+        if (metrics) return cudaMemcpyAsync(d_stage, metrics[m], (size_t)total * 8, cudaMemcpyHostToDevice, c->stream);
+        MetricBuildArgs mb;
+        mb.connijk = d_conn; mb.coords = c->coords; mb.dpsi = d_dpsi; mb.out = d_stage; mb.nelem = E; mb.npoin = N;
+        mb.nsd = c->nsd; mb.ngl = c->ngl; mb.slot = m;
+        k_build_metric<<<nblk(total, 256), 256, 0, c->stream>>>(mb);
+        c->launches++;
+        return cudaGetLastError();
+    };
     RetileArgs ra;
     ra.omega = d_omega; ra.connijk = d_conn; ra.rec = c->rec; ra.nelem = E; ra.nsd = c->nsd; ra.ngl = c->ngl; ra.np = np;
     ra.nmet = c->nmet; ra.npp = (np + 3) / 4 * 4; ra.rec_bytes = c->rec_bytes; ra.src = nullptr;
@@ -452,8 +472,8 @@ extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *c
         ga.slot = -1;
         k_retile_group<<<nblk(total, 256), 256, 0, c->stream>>>(ga);
         for (int m = 0; m < c->nmet; ++m) {
-            if (!metrics[m]) { cleanup(); return fail(c, JX_EINVAL, "metric array %d is null", m); }
-            CKC(cudaMemcpyAsync(d_stage, metrics[m], (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
+            if (metrics && !metrics[m]) { cleanup(); return fail(c, JX_EINVAL, "metric array %d is null", m); }
+            CKC(stage_metric(m));
             ga.src = d_stage; ga.slot = m;
             k_retile_group<<<nblk(total, 256), 256, 0, c->stream>>>(ga);
             CKC(cudaStreamSynchronize(c->stream));
@@ -466,22 +486,13 @@ extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *c
         ra.slot = -1;
         k_retile<<<nblk(total, 256), 256, 0, c->stream>>>(ra);
         for (int m = 0; m < c->nmet; ++m) {
-            if (!metrics[m]) { cleanup(); return fail(c, JX_EINVAL, "metric array %d is null", m); }
-            CKC(cudaMemcpyAsync(d_stage, metrics[m], (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
+            if (metrics && !metrics[m]) { cleanup(); return fail(c, JX_EINVAL, "metric array %d is null", m); }
+            CKC(stage_metric(m));
             ra.src = d_stage; ra.slot = m;
             k_retile<<<nblk(total, 256), 256, 0, c->stream>>>(ra);
             CKC(cudaStreamSynchronize(c->stream));   // host array may be pageable: keep the staging reuse ordered
         }
         c->launches += c->nmet + 1;
-    }
-    // coords: Julia [nsd, N] -> device [nsd][N]
-    if (coords && N > 0) {
-        std::vector<double> soa((size_t)N * c->nsd);
-        for (int d = 0; d < c->nsd; ++d)
-            for (int64_t ip = 0; ip < N; ++ip) soa[(size_t)d * N + ip] = coords[(size_t)ip * c->nsd + d];
-        CKC(cudaMemcpy(c->coords, soa.data(), soa.size() * 8, cudaMemcpyHostToDevice));
-    } else {
-        CKC(cudaMemsetAsync(c->coords, 0, (size_t)std::max<int64_t>(1, N * c->nsd) * 8, c->stream));
     }
     // node -> (element, local) CSR in DSS_rhs! order (element ascending)
     {
@@ -509,6 +520,25 @@ extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *c
     c->have_mesh = true;
     c->rec_layout = c->ks->rec_layout;
     return JX_OK;
+}
+
+}  // namespace
+
+extern "C" int jx_upload_mesh(jx_ctx *c, const int64_t *connijk, const double *coords, const double *const *metrics,
+                              int nmetrics, const double *dpsi, const double *omega, const double *Minv, const double *qe) {
+    if (!c) return JX_EINVAL;
+    if (!c->have_problem) return fail(c, JX_ESTATE, "jx_upload_mesh before jx_set_problem");
+    if (!connijk || !metrics || !dpsi || !omega || !Minv) return fail(c, JX_EINVAL, "jx_upload_mesh: null array");
+    if (nmetrics != c->nmet) return fail(c, JX_EINVAL, "expected %d metric arrays, got %d", c->nmet, nmetrics);
+    return upload_mesh_impl(c, connijk, coords, metrics, dpsi, omega, Minv, qe);
+}
+
+extern "C" int jx_upload_mesh_coords(jx_ctx *c, const int64_t *connijk, const double *coords, const double *dpsi,
+                                     const double *omega, const double *Minv, const double *qe) {
+    if (!c) return JX_EINVAL;
+    if (!c->have_problem) return fail(c, JX_ESTATE, "jx_upload_mesh_coords before jx_set_problem");
+    if (!connijk || !coords || !dpsi || !omega || !Minv) return fail(c, JX_EINVAL, "jx_upload_mesh_coords: null array");
+    return upload_mesh_impl(c, connijk, coords, nullptr, dpsi, omega, Minv, qe);
 }
 
 extern "C" int jx_upload_bcs(jx_ctx *c, int64_t nfaces, const int64_t *poin_in_bdy_face, const double *nx, const double *ny,

@@ -1767,6 +1767,85 @@ static __global__ void k_lincomb(LinArgs a) {
 // interface / periodic assembly (assemble_mpi!, mpi_communications.jl:260-338)
 // buffers are node-major interleaved: buf[i*m + j] = a[idx[i], j]
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// build_metric_terms! on the device (metric_terms.jl:332-474 3D, :197-257 2D).  Thread = (element, local
+// node), element fastest; every thread differentiates the element's coordinates along its three (two) LGL lines --
+// psi is the identity at the LGL points, so the reference's triple sums collapse to single sums over the line --
+// in ascending node order with separate multiply and add, forms the cofactors and the determinant with the
+// reference's association, and writes ONE of the metric arrays (slot) in the reference's element-fastest layout;
+// the record builders (k_retile / k_retile_group) then consume it exactly like a host-supplied array.
+// ------------------------------------------------------------------------------------------
+struct MetricBuildArgs {
+    const int64_t *connijk;   // [E, n, n, n|1], 1-based
+    const double *coords;     // [nsd][npoin]
+    const double *dpsi;       // dpsi[m + n*i] = L'_m(xi_i)
+    double *out;              // [E, n, n, n|1]
+    int64_t nelem, npoin;
+    int nsd, ngl, slot;       // 3D: 0..8 = dxi/dx dxi/dy dxi/dz deta/dx ... dzeta/dz, 9 = Je; 2D: 0..3, 4 = Je
+};
+
+static __global__ void k_build_metric(MetricBuildArgs a) {
+    const int n = a.ngl, nsd = a.nsd;
+    const int np = nsd == 3 ? n * n * n : n * n;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= a.nelem * np) return;
+    const int64_t iel = tid % a.nelem;
+    const int l = (int)(tid / a.nelem);
+    const int i = l % n, j = (l / n) % n, k = l / (n * n);
+    const int lidx[3] = {i, j, k};
+    const int stride[3] = {1, n, n * n};
+    double d[3][3];           // d[c][dir] = d(coordinate c) / d(reference direction dir)
+    for (int dir = 0; dir < nsd; ++dir) {
+        double acc[3] = {0.0, 0.0, 0.0};
+        const int base = l - lidx[dir] * stride[dir];
+        for (int m = 0; m < n; ++m) {
+            const int64_t ip = a.connijk[iel + a.nelem * (int64_t)(base + m * stride[dir])] - 1;
+            const double w = a.dpsi[m + n * lidx[dir]];
+            for (int c = 0; c < nsd; ++c) {
+                const double t = a.coords[(size_t)c * a.npoin + ip] * w;
+                acc[c] = acc[c] + t;
+            }
+        }
+        for (int c = 0; c < nsd; ++c) d[c][dir] = acc[c];
+    }
+    double v;
+    if (nsd == 3) {
+        const double dxdxi = d[0][0], dxdeta = d[0][1], dxdzeta = d[0][2];
+        const double dydxi = d[1][0], dydeta = d[1][1], dydzeta = d[1][2];
+        const double dzdxi = d[2][0], dzdeta = d[2][1], dzdzeta = d[2][2];
+        const double c1 = dydeta * dzdzeta - dydzeta * dzdeta;
+        const double c2 = dxdzeta * dzdeta - dxdeta * dzdzeta;
+        const double c3 = dxdeta * dydzeta - dxdzeta * dydeta;
+        const double Je = (dxdxi * c1 + dydxi * c2) + dzdxi * c3;
+        if (a.slot == 9) v = Je;
+        else {
+            const double Jinv = 1.0 / Je;
+            double cf;
+            switch (a.slot) {
+                case 0: cf = c1; break;
+                case 1: cf = c2; break;
+                case 2: cf = c3; break;
+                case 3: cf = dydzeta * dzdxi - dydxi * dzdzeta; break;
+                case 4: cf = dxdxi * dzdzeta - dxdzeta * dzdxi; break;
+                case 5: cf = dxdzeta * dydxi - dxdxi * dydzeta; break;
+                case 6: cf = dydxi * dzdeta - dydeta * dzdxi; break;
+                case 7: cf = dxdeta * dzdxi - dxdxi * dzdeta; break;
+                default: cf = dxdxi * dydeta - dxdeta * dydxi; break;
+            }
+            v = cf * Jinv;
+        }
+    } else {
+        const double dxdxi = d[0][0], dxdeta = d[0][1], dydxi = d[1][0], dydeta = d[1][1];
+        const double Je = dxdxi * dydeta - dydxi * dxdeta;
+        if (a.slot == 4) v = Je;
+        else {
+            const double Jinv = 1.0 / Je;
+            v = a.slot == 0 ? dydeta * Jinv : a.slot == 1 ? (-dxdeta) * Jinv : a.slot == 2 ? (-dydxi) * Jinv : dxdxi * Jinv;
+        }
+    }
+    a.out[tid] = v;
+}
+
 // interface-first split: nodes named by the assembler lists, then the element groups whose records name one of them
 static __global__ void k_mark_nodes(uint8_t *mask, const int64_t *idx, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -231,6 +231,28 @@ def test_interface_first_split_overlap_3d(lpert):
             p.close()
 
 
+@pytest.mark.parametrize("nsd,nop", [(3, 4), (3, 7), (2, 4), (2, 5)])
+def test_device_built_metrics_bit_exact(nsd, nop):
+    """jx_upload_mesh_coords: the metric terms built on the device from connijk + coords
+    (metric_terms.jl:332-474 / 197-257) give the same rhs! bit for bit as the host arrays the oracle uses, through the
+    team records (3D nop 4), the generic records (3D nop 7) and the 2D records."""
+    spec = box3d((4, 3, 3) if nop < 7 else (3, 2, 2), nop, warp=0.05) if nsd == 3 else box2d((6, 5), nop, warp=0.05)
+    sems, qns, qes, us = euler_case(spec, 1, lpert=False)
+    dus, ub, _ = _oracle_rhs(sems, qes, us, False, True, pow_mode=1)
+    p = jrhs.params_setup(sems[0], qes[0], _inputs(False, True, nsd), pow_mode=1, dss_mode=0, device_metrics=True)
+    try:
+        u = us[0].copy()
+        du = np.empty_like(u)
+        jrhs.rhs_bang(du, u, p, 0.0)
+    finally:
+        p.close()
+    assert np.array_equal(du, dus[0]), rel_err_per_node(du, dus[0])
+    if nsd == 3 and nop == 4:      # inviscid: the warp-team kernel and its lane-major records
+        dus, ub, _ = _oracle_rhs(sems, qes, us, False, False, pow_mode=1)
+        du2, _ = _gpu_rhs(sems, qes, us, False, False, pow_mode=1, dss_mode=0, device_metrics=True)
+        assert np.array_equal(du2, dus[0]), rel_err_per_node(du2, dus[0])
+
+
 # ---- pencil element kernel (JX_OPT_ELEM_KERNEL 1 = exact order, 2 = single partial) ---------------
 @pytest.mark.parametrize("variant", [1, 3, 5, 6, 8, 9])
 @pytest.mark.parametrize("nop", [2, 4, 5])
