@@ -54,11 +54,18 @@ function b200_setup(params, inputs; device = 0, rank = 0, nranks = 1, uid = C_NU
         [metrics.dξdx, metrics.dξdy, metrics.dξdz, metrics.dηdx, metrics.dηdy, metrics.dηdz,
          metrics.dζdx, metrics.dζdy, metrics.dζdz, metrics.Je] :
         [metrics.dξdx, metrics.dξdy, metrics.dηdx, metrics.dηdy, metrics.Je]
-    GC.@preserve mets begin
-        ptrs = Ptr{Float64}[pointer(m) for m in mets]
-        check(c, ccall((:jx_upload_mesh, LIB), Cint,
-                       (Ctx, Ptr{Int64}, Ptr{Float64}, Ptr{Ptr{Float64}}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                       c, mesh.connijk, mesh.coords, ptrs, length(ptrs), basis.dψ, params.ω, params.Minv, params.qp.qe))
+    if get(inputs, :b200_device_metrics, false)
+        # build_metric_terms! on the device from connijk + coords (metric_terms.jl:332-474): same bits, no host arrays read
+        check(c, ccall((:jx_upload_mesh_coords, LIB), Cint,
+                       (Ctx, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       c, mesh.connijk, mesh.coords, basis.dψ, params.ω, params.Minv, params.qp.qe))
+    else
+        GC.@preserve mets begin
+            ptrs = Ptr{Float64}[pointer(m) for m in mets]
+            check(c, ccall((:jx_upload_mesh, LIB), Cint,
+                           (Ctx, Ptr{Int64}, Ptr{Float64}, Ptr{Ptr{Float64}}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                           c, mesh.connijk, mesh.coords, ptrs, length(ptrs), basis.dψ, params.ω, params.Minv, params.qp.qe))
+        end
     end
     kinds = Int32[t in PERIODIC ? 0 : 1 for t in mesh.bdy_face_type]        # BCs.jl:621-623
     if nsd == 3
