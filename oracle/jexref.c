@@ -21,8 +21,12 @@
  * PARITY PINNING: the real reference cannot be executed in this image (no Julia).
  * The restatement is pinned end-to-end against the reference's golden end state
  * test/CI-ref/CompEuler/theta/output/var_{1..4}_0.h5 (tests/test_oracle_golden.py,
- * atol 1e-5 as test/ci_cases.jl:57,73); per-RHS and 3D parity are otherwise unpinned
- * because the reference holds no such vectors.
+ * atol 1e-5 as test/ci_cases.jl:57,73; reproduced to 7e-11) and against
+ * test/CI-ref/AdvDiff/kopriva/output/var_1_0.h5 (2D advection-diffusion, doubly periodic,
+ * SSPRK54: reproduced to 1e-12, which also pins the SSPRK54 stage form, the periodic-twin
+ * assembly and the IC conditioning); per-RHS and 3D parity are otherwise unpinned
+ * because the reference holds no such vectors.  The ShallowWater CI end
+ * state is committed (tests/golden) but not reproduced yet: PARITY UNPINNED for that functor.
  */
 #include <math.h>
 #include <stdint.h>

@@ -43,3 +43,24 @@ def rel_err_per_node(a, b):
 
 
 PHYS = PhysicalConst().packed()
+
+
+def kopriva_case():
+    """problems/AdvDiff/kopriva (the reference's CI case, test/ci_cases.jl:75): 10x20 elements, nop 4, periodic in x and y
+    (kopriva_periodic.msh), Gaussian at (5, 3) (initialize.jl:17-30), wind (0.5, 1) (user_flux.jl:1-16), AV mu = 0.1,
+    PERT with qe = 0, IC conditioned by conformity4ncf_q! (params_setup.jl:259-297 -- this is what makes the periodic
+    twins start from one value).  Returns (sem, qe, u0, phys, inputs)."""
+    from jexpresso_b200.sem.setup import conformity4ncf_q_host
+    spec = box2d((10, 20), 4, periodic=(True, True, False), lo=(0.0, 0.0), hi=(10.0, 20.0))
+    sems = sem_setup(spec, 1)
+    m = sems[0].mesh
+    xc = (m.x.max() + m.x.min()) / 2
+    qn = np.zeros((m.npoin, 2), order="F")
+    a1, a2 = -((m.x - xc) / 1.0) ** 2, -((m.y - 3.0) / 1.0) ** 2
+    qn[:, 0] = 1.0 * np.exp(a1) * np.exp(a2)
+    qe = np.zeros((m.npoin, 2), order="F")
+    conformity4ncf_q_host(sems, [qn], 1)
+    phys = [0.0] * 16
+    phys[8], phys[9] = 0.5, 1.0
+    inputs = {"SOL_VARS_TYPE": "PERT", "lsource": True, "lvisc": True, "mu": [0.1], "dt": 0.005, "ode_solver": "SSPRK54"}
+    return sems[0], qe, np.ascontiguousarray(qn[:, 0]).copy(), phys, inputs

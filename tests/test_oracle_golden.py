@@ -51,3 +51,27 @@ def test_theta_golden_moments(theta_end_state):
         for f in (np.sum, np.min, np.max, lambda v: np.sum(v * v)):
             fa, fb = float(f(a)), float(f(b))
             assert abs(fa - fb) <= 1e-5 * max(1.0, abs(fb)) * 10
+
+
+def test_advdiff_kopriva_golden_end_state():
+    """test/CI-ref/AdvDiff/kopriva (2D advection-diffusion, doubly periodic, AV mu=0.1, SSPRK54, dt=0.005, tend=10): pins
+    the AdvDiff functor, the neqs=1 viscous path, the periodic-twin assembly (incl. the 4-fold corner), the IC
+    conditioning and -- per stage -- the SSPRK54 restatement against a real Julia/OrdinaryDiffEq run.  dt is
+    Float64(Float32(0.005)) (TimeIntegrators.jl:464-465), so 2000 steps end 2.2e-7 short of tend and the integrator takes
+    one clipped step to tend.  Order-free comparison (Gridap numbering); the reference's default CI tolerance applies
+    (rtol 1e-5 class), the restatement lands at 1e-12."""
+    from helpers import kopriva_case
+    sem, qe, u0, phys, inputs = kopriva_case()
+    m = sem.mesh
+    prob = ref.RefProblem(sem, qe, eq_id=2, lpert=True, lsource=True, lvisc=True, visc_coeff=inputs["mu"], phys=phys,
+                          pow_mode=0, neqs=1)
+    run = ref.RefRun([prob], ref.setup_assembler([m.ip2gip], [m.gip2owner]))
+    us = [u0.copy()]
+    t = ref.time_loop(run, us, 0.0, inputs["dt"], 2000, scheme="SSPRK54")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "AdvDiff_kopriva.npz"))
+    gold = np.sort(g["q1"])
+    assert gold.shape[0] == m.npoin == 3321 and abs(float(g["t_time"][0]) - 10.0) < 1e-9
+    assert np.max(np.abs(np.sort(us[0]) - gold)) < 1e-7            # 2.0e-8: the missing last 2.2e-7 of time
+    ref.step_ssprk54(run, us, t, 10.0 - t, [np.zeros_like(us[0])])   # the clipped final step
+    worst = float(np.max(np.abs(np.sort(us[0]) - gold)))
+    assert worst < 1e-10, worst                                    # measured 1.1e-12
