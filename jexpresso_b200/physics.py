@@ -45,3 +45,19 @@ class PhysicalConst:
     def packed(self):
         """Packed array handed to jx_set_problem: [C0, γ, g, Rair, cp, cv, pref, γ-1]."""
         return [self.C0, self.gamma, self.g, self.Rair, self.cp, self.cv, self.pref, self.gamma - 1.0]
+
+
+def swe_packed(g=9.81, h_wet=1.0e-3, cone_height=0.93, sigma_dry=25.0, cone_xc=12.5, cone_yc=0.0, cone_rc=3.6):
+    """Packed constants of the ShallowWater functor (problems/ShallowWater/SoliWaveIsland/user_flux.jl:41-42,
+    user_source.jl:1-5): phys[9] = cone height, [10] = dry-node relaxation rate, [11] = g, [12] = wet/dry film depth,
+    [13],[14] = cone centre, [15] = cone radius."""
+    ph = [0.0] * 16
+    ph[9], ph[10], ph[11], ph[12], ph[13], ph[14], ph[15] = cone_height, sigma_dry, g, h_wet, cone_xc, cone_yc, cone_rc
+    return ph
+
+
+def advdiff_packed(u=0.5, v=1.0, w=0.0):
+    """Packed constants of the AdvDiff functor: the constant wind of problems/AdvDiff/*/user_flux.jl in phys[8..10]."""
+    ph = [0.0] * 16
+    ph[8], ph[9], ph[10] = u, v, w
+    return ph

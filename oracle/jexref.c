@@ -112,6 +112,14 @@ static void user_flux_3d(const jxo_problem *P, double *F, double *G, double *H, 
     }
 }
 
+/* problems/ShallowWater/SoliWaveIsland/user_flux.jl:44-55 _swe_uvel: sqrt(2) Hc Hu / sqrt(Hc^4 + max(Hc, eps)^4);
+ * the fourth powers are formed as (x*x)*(x*x), the form the device functor uses (Julia's x^4 is within an ulp of it) */
+static inline double swe_uvel(double eps, double Hc, double Hu) {
+    double H4 = fmax(Hc, eps);
+    double a = (Hc * Hc) * (Hc * Hc), b = (H4 * H4) * (H4 * H4);
+    return sqrt(2.0) * Hc * Hu / sqrt(a + b);
+}
+
 /* problems/CompEuler/theta/user_flux.jl:1-52 ; kelvinHelmholtzChan2022/user_flux.jl:30-48 ;
  * AdvDiff/kopriva/user_flux.jl:1-16 ; ShallowWater/SoliWaveIsland/user_flux.jl */
 static void user_flux_2d(const jxo_problem *P, double *F, double *G, const double *q, const double *qe) {
@@ -136,17 +144,41 @@ static void user_flux_2d(const jxo_problem *P, double *F, double *G, const doubl
     } else if (P->eq_id == JXO_EQ_ADVDIFF) {
         F[0] = P->phys[8] * q[0];
         G[0] = P->phys[9] * q[0];
+    } else if (P->eq_id == JXO_EQ_SHALLOW_WATER) {
+        /* problems/ShallowWater/SoliWaveIsland/user_flux.jl:44-86 (TOTAL; PERT forwards to it): clamped depth,
+         * desingularised velocity, perturbation pressure g (H^2 - He^2)/2.  phys[11] = g, phys[12] = wet/dry film depth */
+        double g = P->phys[11], eps = P->phys[12];
+        double Hc = fmax(q[0], 0.0), He = qe[0];
+        double u = swe_uvel(eps, Hc, q[1]), v = swe_uvel(eps, Hc, q[2]);
+        double p = 0.5 * g * (Hc * Hc - He * He);
+        F[0] = Hc * u; F[1] = Hc * u * u + p; F[2] = Hc * u * v;
+        G[0] = Hc * v; G[1] = Hc * v * u; G[2] = Hc * v * v + p;
     }
-    (void)qe;
 }
 
 /* problems/CompEuler/3d/user_source.jl:1-66, problems/CompEuler/theta/user_source.jl:1-49:
  * S[vertical momentum] = -ρ g with ρ = q[1] for both TOTAL and PERT */
-static void user_source(const jxo_problem *P, double *S, const double *q) {
+static void user_source(const jxo_problem *P, double *S, const double *q, const double *qe, const double *xyz) {
     for (int e = 0; e < P->neqs; ++e) S[e] = 0.0;
     if (P->eq_id == JXO_EQ_EULER_THETA) {
         double r = q[0];
         S[P->nsd] = -r * P->phys[2];
+    } else if (P->eq_id == JXO_EQ_SHALLOW_WATER) {
+        /* problems/ShallowWater/SoliWaveIsland/user_source.jl:34-73: -g (H - He) grad(Hb) over the conical island
+         * (phys[9] = cone height, [13],[14] = centre, [15] = radius) and the dry-node momentum relaxation (phys[10]) */
+        double g = P->phys[11], eps = P->phys[12];
+        double H = q[0];
+        double dH = fmax(H, 0.0) - qe[0];
+        double dx = xyz[0] - P->phys[13], dy = xyz[1] - P->phys[14];
+        double r = sqrt(dx * dx + dy * dy);
+        double bx = 0.0, by = 0.0;
+        if (r < P->phys[15] && r > 1.0e-12) {
+            double slope = -P->phys[9] / (P->phys[15] * r);
+            bx = slope * dx; by = slope * dy;
+        }
+        S[1] = -g * dH * bx;
+        S[2] = -g * dH * by;
+        if (H < eps) { S[1] = S[1] - P->phys[10] * q[1]; S[2] = S[2] - P->phys[10] * q[2]; }
     }
 }
 
@@ -162,6 +194,10 @@ static void user_primitives(const jxo_problem *P, const double *u, const double 
             for (int e = 1; e < q - 1; ++e) up[e] = u[e] / (u[0] + qe[0]);
             up[q - 1] = (u[q - 1] + qe[q - 1]) / (u[0] + qe[0]) - qe[q - 1] / qe[0];
         }
+    } else if (P->eq_id == JXO_EQ_SHALLOW_WATER) {
+        /* problems/ShallowWater/SoliWaveIsland/user_primitives.jl:14-18: (H - He, Hu, Hv) */
+        up[0] = u[0] - qe[0];
+        for (int e = 1; e < q; ++e) up[e] = u[e];
     } else {
         for (int e = 0; e < q; ++e) up[e] = u[e];
     }
@@ -293,7 +329,8 @@ static void inviscid_rhs_el_3d(const jxo_problem *P, jxo_work *W) {
             user_flux_3d(P, f, g, h, ql, qel);
             for (int e = 0; e < q; ++e) { LOC4(F, i, j, k, e) = f[e]; LOC4(G, i, j, k, e) = g[e]; LOC4(H, i, j, k, e) = h[e]; }
             if (P->lsource) {
-                user_source(P, s, ql);
+                double xyz[3] = {P->coords[0 + 3 * ip], P->coords[1 + 3 * ip], P->coords[2 + 3 * ip]};
+                user_source(P, s, ql, qel, xyz);
                 for (int e = 0; e < q; ++e) LOC4(S, i, j, k, e) = s[e];
             }
         }
@@ -352,7 +389,8 @@ static void inviscid_rhs_el_2d(const jxo_problem *P, jxo_work *W) {
             user_flux_2d(P, f, g, ql, qel);
             for (int e = 0; e < q; ++e) { LOC3(F, i, j, e) = f[e]; LOC3(G, i, j, e) = g[e]; }
             if (P->lsource) {
-                user_source(P, s, ql);
+                double xyz[3] = {P->coords[0 + 2 * ip], P->coords[1 + 2 * ip], 0.0};
+                user_source(P, s, ql, qel, xyz);
                 for (int e = 0; e < q; ++e) LOC3(S, i, j, e) = s[e];
             }
         }

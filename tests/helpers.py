@@ -60,7 +60,35 @@ def kopriva_case():
     qn[:, 0] = 1.0 * np.exp(a1) * np.exp(a2)
     qe = np.zeros((m.npoin, 2), order="F")
     conformity4ncf_q_host(sems, [qn], 1)
-    phys = [0.0] * 16
-    phys[8], phys[9] = 0.5, 1.0
+    from jexpresso_b200.physics import advdiff_packed
+    phys = advdiff_packed(0.5, 1.0)
     inputs = {"SOL_VARS_TYPE": "PERT", "lsource": True, "lvisc": True, "mu": [0.1], "dt": 0.005, "ode_solver": "SSPRK54"}
     return sems[0], qe, np.ascontiguousarray(qn[:, 0]).copy(), phys, inputs
+
+
+def soliwave_case(nel=(25, 30)):
+    """problems/ShallowWater/SoliWaveIsland (the reference's CI case, test/ci_cases.jl:79): [0,25] x [-15,15], 25 x 30
+    elements, nop 4, free-slip walls, solitary wave over a conical island (initialize.jl:47-100), TOTAL, AV mu = 0.05.
+    Returns (sem, qn, qe, u0, phys, inputs); smaller ``nel`` gives the same set-up on a coarser mesh (functor tests)."""
+    from jexpresso_b200.physics import swe_packed
+    spec = box2d(nel, 4, lo=(0.0, -15.0), hi=(25.0, 15.0))
+    sems = sem_setup(spec, 1)
+    m = sems[0].mesh
+    g, A, h0, xc_wave = 9.81, 0.064, 0.32, 2.5
+    gam = np.sqrt(3.0 * A / (4.0 * h0 ** 3))
+    xc, yc, rc, hc, H_dry = 12.5, 0.0, 3.6, 0.93, 1.0e-3
+    sech = 1.0 / np.cosh(gam * (m.x - xc_wave))
+    eta = A * sech * sech
+    dx, dy = m.x - xc, m.y - yc
+    r = np.sqrt(dx * dx + dy * dy)
+    Hb = np.where(r < rc, hc * (1.0 - r / rc), 0.0)
+    Hw = np.maximum(h0 + eta - Hb, H_dry)
+    ux = np.where(Hw > H_dry, np.sqrt(g * (h0 + eta)) * eta / (h0 + eta), 0.0)
+    qn = np.zeros((m.npoin, 4), order="F")
+    qe = np.zeros((m.npoin, 4), order="F")
+    qn[:, 0], qn[:, 1] = Hw, Hw * ux
+    qe[:, 0] = np.maximum(h0 - Hb, H_dry)
+    inputs = {"SOL_VARS_TYPE": "TOTAL", "lsource": True, "lvisc": True, "mu": [0.05, 0.05, 0.05], "dt": 0.01,
+              "ode_solver": "SSPRK54"}
+    u0 = np.ascontiguousarray(qn[:, :3].reshape(-1, order="F"))
+    return sems[0], qn, qe, u0, swe_packed(), inputs
