@@ -25,8 +25,9 @@
  * test/CI-ref/AdvDiff/kopriva/output/var_1_0.h5 (2D advection-diffusion, doubly periodic,
  * SSPRK54: reproduced to 1e-12, which also pins the SSPRK54 stage form, the periodic-twin
  * assembly and the IC conditioning); per-RHS and 3D parity are otherwise unpinned
- * because the reference holds no such vectors.  The ShallowWater CI end
- * state is committed (tests/golden) but not reproduced yet: PARITY UNPINNED for that functor.
+ * because the reference holds no such vectors.  The ShallowWater functor is
+ * pinned on test/CI-ref/ShallowWater/SoliWaveIsland within the reference's atol 1e-5 (bulk
+ * 1e-9; wet/dry-front nodes up to 5e-6).  PARITY UNPINNED: the total-energy functor (no vector).
  */
 #include <math.h>
 #include <stdint.h>

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import MU2, box2d, euler_case, kopriva_case
+from helpers import MU2, box2d, euler_case
 from jexpresso_b200 import capi
 from jexpresso_b200 import rhs as jrhs
 
@@ -40,23 +40,3 @@ def test_theta_golden_end_state_on_gpu(graph):
         worst = max(worst, float(np.max(np.abs(mine - gold))))
         assert np.allclose(mine, gold, rtol=0.0, atol=1e-5), f"variable {i + 1} outside the reference's CI tolerance"
     assert worst < 1e-7, worst      # the CPU restatement sits at 7e-11 of the Julia run; the GPU evaluates the same sequence
-
-
-def test_advdiff_kopriva_golden_end_state_on_gpu():
-    """test/CI-ref/AdvDiff/kopriva through the CUDA path: AdvDiff functor, neqs = 1 viscous pass, periodic twins through the
-    assembler self lists, SSPRK54 via jx_step, then the integrator's clipped final step to tend = 10 (see
-    tests/test_oracle_golden.py::test_advdiff_kopriva_golden_end_state, where the CPU restatement lands at 1e-12)."""
-    from jexpresso_b200.physics import SCHEME_SSPRK54
-    sem, qe, u0, phys, inputs = kopriva_case()
-    p = jrhs.params_setup(sem, qe, inputs, eqs="AdvDiff", phys=phys, pow_mode=1, dss_mode=0)
-    try:
-        u = u0.copy()
-        t = jrhs.time_loop_bang(inputs, p, u, 2000)
-        p.ctx.set_state(u)
-        p.ctx.step(SCHEME_SSPRK54, t, 10.0 - t, 1)
-        u = p.ctx.get_state()
-    finally:
-        p.close()
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "AdvDiff_kopriva.npz"))
-    worst = float(np.max(np.abs(np.sort(u) - np.sort(g["q1"]))))
-    assert worst < 1e-9, worst
