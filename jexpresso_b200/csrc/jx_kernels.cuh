@@ -225,6 +225,16 @@ struct ElemArgs {
     double dpsi[64];       // Julia dψ[m,i] column-major: dpsi[m + NGL*i]
 };
 
+// functors that add the viscous-work term to one equation of the 2D AV pass declare TAU_U_EQ
+template <class EQ, class = void>
+struct has_tau_u : std::false_type {};
+template <class EQ>
+struct has_tau_u<EQ, std::void_t<decltype(EQ::TAU_U_EQ)>> : std::true_type {};
+template <class EQ, bool = has_tau_u<EQ>::value>
+struct tau_u_eq { static constexpr int value = -1; };
+template <class EQ>
+struct tau_u_eq<EQ, true> { static constexpr int value = EQ::TAU_U_EQ; };
+
 template <int NSD, int NGL, class EQ, bool VISC, int EPB>
 struct ElemNodeCfg {
     using G = Geo<NSD, NGL>;
@@ -421,8 +431,32 @@ k_elem_node(const __grid_constant__ ElemArgs a) {
                         const double dqdx = mu * auxi;
                         auxi = dqdxi * mt[1] + dqdeta * mt[3];
                         const double dqdy = mu * auxi;
-                        Gv[0 * NP + l] = (mt[0] * dqdx + mt[1] * dqdy) * wJ;
-                        Gv[1 * NP + l] = (mt[2] * dqdx + mt[3] * dqdy) * wJ;
+                        double flux_x = dqdx, flux_y = dqdy;
+                        if constexpr (has_tau_u<EQ>::value) {
+                            if (e == tau_u_eq<EQ>::value) {          // total-energy form: viscous work, rhs.jl:1988, 2018-2041
+                                const double *Uu = sU + ((size_t)slot * NEQ + 1) * NP, *Uv = sU + ((size_t)slot * NEQ + 2) * NP;
+                                double dudxi = 0, dudeta = 0, dvdxi = 0, dvdeta = 0;
+#pragma unroll
+                                for (int m = 0; m < NGL; ++m) {
+                                    dudxi = fma(sD[m + NGL * i], Uu[m + NGL * j], dudxi);
+                                    dudeta = fma(sD[m + NGL * j], Uu[i + NGL * m], dudeta);
+                                    dvdxi = fma(sD[m + NGL * i], Uv[m + NGL * j], dvdxi);
+                                    dvdeta = fma(sD[m + NGL * j], Uv[i + NGL * m], dvdeta);
+                                }
+                                const double dudx = dudxi * mt[0] + dudeta * mt[2], dudy = dudxi * mt[1] + dudeta * mt[3];
+                                const double dvdx = dvdxi * mt[0] + dvdeta * mt[2], dvdy = dvdxi * mt[1] + dvdeta * mt[3];
+                                const double div_u = dudx + dvdy;
+                                const double mu2 = a.visc[1];
+                                const double txx = 2.0 * mu2 * dudx - (2.0 / 3.0) * mu2 * div_u;
+                                const double tyy = 2.0 * mu2 * dvdy - (2.0 / 3.0) * mu2 * div_u;
+                                const double txy = mu2 * (dudy + dvdx);
+                                const double ul = Uu[l], vl = Uv[l];
+                                flux_x = flux_x + (txx * ul + txy * vl);
+                                flux_y = flux_y + (txy * ul + tyy * vl);
+                            }
+                        }
+                        Gv[0 * NP + l] = (mt[0] * flux_x + mt[1] * flux_y) * wJ;
+                        Gv[1 * NP + l] = (mt[2] * flux_x + mt[3] * flux_y) * wJ;
                     }
                 }
             }

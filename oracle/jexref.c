@@ -27,7 +27,10 @@
  * assembly and the IC conditioning); per-RHS and 3D parity are otherwise unpinned
  * because the reference holds no such vectors.  The ShallowWater functor is
  * pinned on test/CI-ref/ShallowWater/SoliWaveIsland within the reference's atol 1e-5 (bulk
- * 1e-9; wet/dry-front nodes up to 5e-6).  PARITY UNPINNED: the total-energy functor (no vector).
+ * 1e-9; wet/dry-front nodes up to 5e-6).  PARITY UNPINNED: the total-energy functor (the reference holds no
+ * golden vector for kelvinHelmholtzChan2022; its flux, primitives (ρ,u,v,T) and τ·u term are restated from
+ * user_flux.jl:30-48, user_primitives.jl:17-23 and rhs.jl:1988, 2018-2041 and checked against an independent
+ * numpy transcription in tests/test_energy_functor_cpu.py).
  */
 #include <math.h>
 #include <stdint.h>
@@ -199,6 +202,15 @@ static void user_primitives(const jxo_problem *P, const double *u, const double 
         /* problems/ShallowWater/SoliWaveIsland/user_primitives.jl:14-18: (H - He, Hu, Hv) */
         up[0] = u[0] - qe[0];
         for (int e = 1; e < q; ++e) up[e] = u[e];
+    } else if (P->eq_id == JXO_EQ_EULER_ENERGY) {
+        /* problems/CompEuler/kelvinHelmholtzChan2022/user_primitives.jl:17-23 (TOTAL, energy_equation != "theta"):
+         * p = γm1*(ρE - 0.5f0*(ρu^2 + ρv^2)/ρ)  [Julia: ((0.5*(ρu*ρu + ρv*ρv))/ρ)];  (ρ, ρu/ρ, ρv/ρ, T = p/(ρ*Rair)) */
+        double r = u[0], ru = u[1], rv = u[2], rE = u[3];
+        double p = P->phys[7] * (rE - 0.5 * (ru * ru + rv * rv) / r);
+        up[0] = r;
+        up[1] = ru / r;
+        up[2] = rv / r;
+        up[3] = p / (r * P->phys[3]);
     } else {
         for (int e = 0; e < q; ++e) up[e] = u[e];
     }

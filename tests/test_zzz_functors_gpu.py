@@ -7,9 +7,9 @@ The last test runs the AdvDiff/kopriva CI case (2000 SSPRK54 steps + the clipped
 CUDA path itself to the reference's golden end state.  The file sorts last so that nothing here can disturb the hard
 assertions of the other GPU files.
 
-These functors had no GPU test while this round's GPU minutes lasted: the tests below were written afterwards, so their
-first execution is the round-end suite.  They are marked xfail(strict=False) for exactly that reason -- an XPASS in the log
-is a pass, an XFAIL is a finding for the next round -- and the marks go once a GPU run has confirmed them."""
+The total-energy functor differentiates (rho, u, v, T) and carries the viscous-work term tau.u on its energy equation
+(kelvinHelmholtzChan2022/user_primitives.jl:17-23, rhs.jl:1988, 2018-2041); its oracle twin is cross-checked against an
+independent numpy transcription in tests/test_energy_functor_cpu.py.  Every test here is a hard assertion."""
 import os
 
 import numpy as np
@@ -21,8 +21,7 @@ from jexpresso_b200.physics import advdiff_packed
 from jexpresso_b200.sem import sem_setup
 from oracle import ref
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first GPU execution of these functors is the round-end suite")]
+pytestmark = pytest.mark.gpu
 
 
 def _compare(sem, qe, u0, neqs, eq_id, eqs, phys, inputs, caches=None):
