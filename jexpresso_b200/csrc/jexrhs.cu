@@ -103,7 +103,9 @@ struct jx_ctx {
     // device arrays
     double *u = nullptr, *du = nullptr, *tmp = nullptr, *qe = nullptr, *Minv = nullptr, *coords = nullptr;
     double *rhs_el = nullptr, *rhs_el_visc = nullptr;
-    double *aux = nullptr;           // per-node flux ingredient (k_node_aux), kernels with launch_aux only
+    double *aux = nullptr;           // per-node flux ingredient (k_node_aux) or node image (k_node_image)
+    size_t aux_doubles = 0;
+    double row_runs_per_elem = 0.0;  // k_elem_team2: bulk copies per element after merging consecutive node ids
     char *rec = nullptr;
     int64_t *n2e_ptr = nullptr;
     uint32_t *n2e_idx = nullptr;
@@ -219,7 +221,7 @@ void free_split(jx_ctx *c) {
 void free_mesh(jx_ctx *c) {
     free_split(c);
     dfree(c->u); dfree(c->du); dfree(c->tmp); dfree(c->qe); dfree(c->Minv); dfree(c->coords);
-    dfree(c->rhs_el); dfree(c->rhs_el_visc); dfree(c->aux); dfree(c->rec); dfree(c->n2e_ptr); dfree(c->n2e_idx);
+    dfree(c->rhs_el); dfree(c->rhs_el_visc); dfree(c->aux); c->aux_doubles = 0; dfree(c->rec); dfree(c->n2e_ptr); dfree(c->n2e_idx);
     for (auto &p : c->ss) dfree(p);
     c->have_mesh = false;
     c->rec_layout = -1;
@@ -247,7 +249,7 @@ int select_kernels(jx_ctx *c) {
     if (c->elem_variant == JX_ELEM_AUTO) {
         // fastest exact-order kernel that exists for this configuration: the warp-team kernels (bit-identical to the
         // generic one), else the generic thread-per-node kernel.  Resident records pin the choice to their layout.
-        const int order[] = {9, 8, 0};
+        const int order[] = {10, 9, 8, 0};
         for (int v : order) {
             ks = lookup(v);
             if (ks && (!c->have_mesh || ks->rec_layout == c->rec_layout)) break;
@@ -391,6 +393,44 @@ extern "C" int jx_set_problem(jx_ctx *c, int nsd, int ngl, int neqs, int64_t nel
 // ------------------------------------------------------------------------------------------
 namespace {
 
+// Row-run tables of the pair records (k_elem_team2).  Per element: its node ids in ascending order are the rows of its
+// node-image tile; wpos[n] = row of flux-view node n; consecutive ids form one run = one bulk copy.  With the
+// reference's numbering (vertices, then the interior nodes of every edge, face and volume as contiguous blocks,
+// mesh.jl:4084+, 4555+, 4944+) a hexahedron of order 4 has at most 27 runs instead of 125 single rows.
+int build_row_runs(jx_ctx *c, const int64_t *connijk) {
+    const KernelSet *ks = c->ks;
+    const int64_t E = c->nelem;
+    const int np = c->np, epb = ks->elems_per_block, maxrun = ks->maxrun;
+    const int64_t ngroups = (E + epb - 1) / epb;
+    const size_t ext = (size_t)ks->group_bytes - ks->wpos_off;
+    std::vector<unsigned char> tab((size_t)ngroups * ext, 0);
+    std::vector<std::pair<int64_t, int>> ids((size_t)np);
+    int64_t total_runs = 0;
+    for (int64_t iel = 0; iel < E; ++iel) {
+        const int64_t g = iel / epb;
+        const int s = (int)(iel % epb);
+        unsigned char *rec = tab.data() + (size_t)g * ext;
+        unsigned char *wpos = rec;
+        int32_t *runi = reinterpret_cast<int32_t *>(rec + (ks->runi_off - ks->wpos_off)) + (size_t)s * maxrun;
+        unsigned char *runr = rec + (ks->runr_off - ks->wpos_off) + (size_t)s * maxrun;
+        unsigned char *runl = rec + (ks->runl_off - ks->wpos_off) + (size_t)s * maxrun;
+        int32_t *nrun = reinterpret_cast<int32_t *>(rec + (ks->nrun_off - ks->wpos_off));
+        for (int l = 0; l < np; ++l) ids[l] = {connijk[(size_t)iel + (size_t)E * l] - 1, l};
+        std::sort(ids.begin(), ids.end());
+        int nr = 0;
+        for (int r = 0; r < np; ++r) {
+            wpos[s * np + ids[r].second] = (unsigned char)r;
+            if (r > 0 && ids[r].first == ids[r - 1].first + 1 && runl[nr - 1] < 255) runl[nr - 1]++;
+            else { runi[nr] = (int32_t)ids[r].first; runr[nr] = (unsigned char)r; runl[nr] = 1; ++nr; }
+        }
+        nrun[s] = nr;
+        total_runs += nr;
+    }
+    c->row_runs_per_elem = E > 0 ? (double)total_runs / (double)E : 0.0;
+    CK(cudaMemcpy2D(c->rec + ks->wpos_off, (size_t)ks->group_bytes, tab.data(), ext, ext, (size_t)ngroups, cudaMemcpyHostToDevice));
+    return JX_OK;
+}
+
 // metrics == nullptr: the metric arrays are built on the device from coords (k_build_metric) instead of uploaded
 int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, const double *const *metrics,
                      const double *dpsi, const double *omega, const double *Minv, const double *qe) {
@@ -481,6 +521,11 @@ int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, co
         ga.slot = -2;                                  // -(omega*J*Minv): needs the ids, omega*J and Minv in place
         k_retile_group<<<nblk(total, 256), 256, 0, c->stream>>>(ga);
         c->launches += c->nmet + 2;
+        if (ks->maxrun > 0) {
+            CKC(cudaStreamSynchronize(c->stream));
+            const int rr = build_row_runs(c, connijk);
+            if (rr) { cleanup(); return rr; }
+        }
     } else if (total > 0) {
         CKC(cudaMemsetAsync(c->rec, 0, rec_total, c->stream));
         ra.slot = -1;
@@ -833,9 +878,25 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     // pass over du.  The deterministic mode keeps the reference order (exchange, then divide_by_mass_matrix!).
     const bool fold_minv = atomics;
     ea.aux = nullptr;
-    if (ks->launch_aux) {                                                // per-node flux ingredient (+ zero-fill of du)
+    if (ks->launch_image) {                                              // node image rows (+ zero-fill of du)
         PhaseScope ps(c, PH_AUX);
-        if (!c->aux) { int rc = dalloc(c, &c->aux, (size_t)N * 4); if (rc) return rc; }   // up to 4 values per node
+        if (!c->aux || c->aux_doubles < (size_t)N * ks->img_rowd) {
+            int rc = dalloc(c, &c->aux, (size_t)N * ks->img_rowd);
+            if (rc) return rc;
+            c->aux_doubles = (size_t)N * ks->img_rowd;
+        }
+        ImageArgs ia;
+        ia.u = u; ia.qe = c->qe; ia.img = c->aux; ia.zero = atomics ? du : nullptr; ia.npoin = N; ia.rowd = ks->img_rowd; ia.phys = c->phys;
+        ks->launch_image(ia, (int)std::min<int64_t>((N + 255) / 256, (int64_t)c->num_sms * 8), s);
+        c->launches++;
+        ea.aux = c->aux;
+    } else if (ks->launch_aux) {                                                // per-node flux ingredient (+ zero-fill of du)
+        PhaseScope ps(c, PH_AUX);
+        if (!c->aux || c->aux_doubles < (size_t)N * 4) {                 // up to 4 values per node
+            int rc = dalloc(c, &c->aux, (size_t)N * 4);
+            if (rc) return rc;
+            c->aux_doubles = (size_t)N * 4;
+        }
         AuxArgs aa;
         aa.u = u; aa.qe = c->qe; aa.aux = c->aux; aa.zero = atomics ? du : nullptr; aa.npoin = N; aa.phys = c->phys;
         ks->launch_aux(aa, (int)std::min<int64_t>((N + 255) / 256, (int64_t)c->num_sms * 8), s);

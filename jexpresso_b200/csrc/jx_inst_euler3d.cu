@@ -31,9 +31,17 @@ namespace jx {
     JX_TSET(NGL, ZW, PW, VAR, false, false), JX_TSET(NGL, ZW, PW, VAR, false, true), JX_TSET(NGL, ZW, PW, VAR, true, false), \
     JX_TSET(NGL, ZW, PW, VAR, true, true)
 
+#define JX_T2SET(NGL, VAR, PERT, POW) make_team2_set<NGL, EulerTheta<3, PERT, POW>, (VAR) == 11>(JX_EQ_EULER_THETA, PERT, POW, VAR)
+
 const KernelSet *lookup_euler_theta_3d(int ngl, int lpert, int jxpow, int lvisc, int variant) {
+#ifdef JX_MIN_BUILD   // kernel experiments: nop 4, TOTAL, jx_pow only -- generic, team (9) and team2 (10)
+    static const KernelSet table[] = {JX_SET(5, false, true, false), JX_SET(5, false, true, true), JX_TSET(5, 2, 2, 9, false, true),
+                                      JX_T2SET(5, 10, false, true), JX_T2SET(5, 11, false, true)};
+#else
     static const KernelSet table[] = {JX_ROW(3), JX_ROW(5), JX_ROW(6), JX_ROW(8), JX_PROW(3), JX_PROW(5), JX_WROW(3), JX_WROW(5), JX_WROW(6),
-                                      JX_GROW(3, 7, 5), JX_GROW(5, 5, 5), JX_GROW(5, 1, 6), JX_TROW(3, 3, 1, 8), JX_TROW(5, 2, 1, 8), JX_TROW(5, 2, 2, 9)};
+                                      JX_GROW(3, 7, 5), JX_GROW(5, 5, 5), JX_GROW(5, 1, 6), JX_TROW(3, 3, 1, 8), JX_TROW(5, 2, 1, 8), JX_TROW(5, 2, 2, 9),
+                                      JX_T2SET(5, 10, false, false), JX_T2SET(5, 10, false, true), JX_T2SET(5, 11, false, false), JX_T2SET(5, 11, false, true)};
+#endif
     for (const KernelSet &k : table)
         if (k.ngl == ngl && k.lpert == lpert && k.jxpow == jxpow && k.lvisc == lvisc && k.variant == variant) return &k;
     return nullptr;

@@ -23,6 +23,10 @@ struct KernelSet {
     void (*launch_bc)(const BcArgs &, cudaStream_t);
     void (*launch_gather)(const GatherArgs &, cudaStream_t);
     void (*launch_aux)(const AuxArgs &, int grid, cudaStream_t);   // nullptr unless the element kernel reads ElemArgs::aux
+    // k_elem_team2: ElemArgs::aux is the node image [npoin][img_rowd] written by launch_image (img_rowd = 0: no image)
+    void (*launch_image)(const ImageArgs &, int grid, cudaStream_t) = nullptr;
+    int img_rowd = 0;
+    int wpos_off = 0, runi_off = 0, runr_off = 0, runl_off = 0, nrun_off = 0, maxrun = 0;   // row-run tables of the pair records
     // rec_layout 4 (group records of k_elem_gpencil): bytes per group, lane columns, id offsets, lane encoders
     int group_bytes = 0, group_nt = 0, zid_off = 0, fid_off = 0, z_off = 0;
     int group_mult[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // [pass][digit]: lane = s*m0 + c0*m1 + c1*m2

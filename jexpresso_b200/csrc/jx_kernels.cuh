@@ -1385,7 +1385,15 @@ struct ElemTeamCfg {
     static constexpr int Z_OFF = 2 * NC * 32 * 8;
     static constexpr int ZID_OFF = Z_OFF + EPB * NSTRZ * 32 * 8;
     static constexpr int FID_OFF = ZID_OFF + EPB * NGL * 32 * 4;
-    static constexpr int GROUP_BYTES = round_up(FID_OFF + NNODE * 4, 128);
+    // k_elem_team2 extension (built on the host by build_row_runs, jexrhs.cu): the node-image rows of an element are
+    // fetched in ascending node-id order, consecutive ids merged into one bulk copy ("run")
+    static constexpr int MAXRUN = round_up(NP, 4);
+    static constexpr int WPOS_OFF = FID_OFF + round_up(NNODE * 4, 16);          // uint8[NNODE]: row (within its element) of flux-view node n
+    static constexpr int RUNI_OFF = WPOS_OFF + round_up(NNODE, 16);             // int32[EPB][MAXRUN]: first node id of the run
+    static constexpr int RUNR_OFF = RUNI_OFF + EPB * MAXRUN * 4;                // uint8[EPB][MAXRUN]: first row of the run
+    static constexpr int RUNL_OFF = RUNR_OFF + EPB * MAXRUN;                    // uint8[EPB][MAXRUN]: rows in the run
+    static constexpr int NRUN_OFF = RUNL_OFF + EPB * MAXRUN;                    // int32[EPB]
+    static constexpr int GROUP_BYTES = round_up(NRUN_OFF + EPB * 4, 128);
 };
 
 // DYN = true: the launch walks a LIST of groups (a.glist) handed out through an atomic counter instead of the static
@@ -1924,3 +1932,5 @@ static __global__ void k_add_sel(double *a, int64_t npoin, int m, const int64_t 
 }
 
 }  // namespace jx
+
+#include "jx_team2.cuh"

@@ -5,7 +5,7 @@ partition; rank r compares its result with the oracle's all-ranks restatement (c
 Deterministic DSS: bit-exact; atomics DSS (bench configuration, team kernel): <= 1e-12 per node, <= 1e-10 L2.
 The last case runs the interface-first split (JX_OPT_OVERLAP: exchange on a second stream beside the interior launch,
 CK2N54 steps replayed as a CUDA graph).  JX_MGPU_CASES="3" (comma separated indices) selects cases.
-Not collected by pytest (needs torchrun); the CPU suite covers the same partition / assembler lists over gloo."""
+Run under the driver by tests/test_zzzz_mgpu_nccl.py (two ranks); the CPU suite covers the same partition / assembler lists over gloo."""
 import os
 import sys
 

@@ -293,6 +293,26 @@ def test_pencil_kernel_atomics(variant, lpert):
         assert pn <= bar and l2 <= 1e-10, (variant, lpert, e, pn, l2)
 
 
+@pytest.mark.parametrize("nel", [(5, 3, 3), (13, 11, 9), (21, 19, 21)])
+def test_team2_kernel_bit_exact(nel):
+    """k_elem_team2 (variant 10: node image + TMA row gathers, ring of equation slots, producer/consumer barriers):
+    same order of every sum as the reference, so bit-exact against the oracle.  Odd element counts leave a ragged last
+    pair; 8379 elements give every CTA of the persistent grid (148 SMs x 4) seven pairs, so the slot ring goes once
+    round and the two-buffer hand-shakes wrap many times."""
+    spec = box3d(nel, 4, warp=0.05)
+    sems, qns, qes, us = euler_case(spec, 1, lpert=False)
+    dus, ub, _ = _oracle_rhs(sems, qes, us, False, False, pow_mode=1)
+    du, u = _gpu_rhs(sems, qes, us, False, False, pow_mode=1, dss_mode=0, elem_kernel=10)
+    assert np.array_equal(u, ub[0])
+    assert np.array_equal(du, dus[0]), rel_err_per_node(du, dus[0])
+    # the bench configuration: RED.ADD scatter with M^-1 folded into the weight
+    du, u = _gpu_rhs(sems, qes, us, False, False, pow_mode=1, dss_mode=1, elem_kernel=10)
+    N = sems[0].mesh.npoin
+    for e in range(5):
+        pn, l2 = rel_err_per_node(du[e * N:(e + 1) * N], dus[0][e * N:(e + 1) * N])
+        assert pn <= 1e-12 and l2 <= 1e-10, (e, pn, l2)
+
+
 def test_pencil_kernel_requires_layout_before_upload():
     """Variant 1/2 read a different element-record layout: switching after the upload is refused."""
     from jexpresso_b200 import capi
