@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- GDOF/s per explicit-RHS evaluation of 3D CompEuler (theta form, nop=4) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nel 73] [--nop 4] [--visc]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c5|c2|c3|c4] [--nel 73] [--nop 4] [--visc]
+
+--config picks one of BASELINE.json's configurations: c5 (default) = synthetic weak-scaling mesh, nel^3 elements nop 4 (or 7)
+per GPU, the configuration the metric is quoted on; c2 = 3D rising bubble 10^3 elements nop 4 with AV; c3 = 2D density-current
+box 128 x 32 elements nop 5 with AV; c4 = 64 x 64 x 24 elements nop 4, periodic x,y, AV, STRONG scaling over the ranks.
 
 A "step" is ONE evaluation of rhs!(du,u,params,t) (boundary projection, fused per-element flux +
 divergence kernel, DSS, interface exchange when N>1, M^-1) on the synthetic weak-scaling mesh of
@@ -109,37 +113,70 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-def build_problem(nel, nop, lpert, rank, nranks, warp=0.05, periodic=False):
-    """This rank's SEM bundle + conditioned IC for the weak-scaling box (nel^3 elements per GPU)."""
-    from helpers import box3d
+def build_problem(nel, nop, lpert, rank, nranks, warp=0.05, periodic=False, config="c5"):
+    """This rank's SEM bundle + conditioned IC.  c5: weak-scaling box (nel^3 elements per GPU); c2 / c3 / c4: the fixed
+    meshes of BASELINE.json configs[1..3], partitioned over the ranks like the reference's _compute_xy_partition."""
+    from helpers import box2d, box3d
     from jexpresso_b200.sem import rtb_initial_state
     from jexpresso_b200.sem.scalable import conformity4ncf_q_rank, sem_setup_rank
-    px, py = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[nranks]
     L = 10000.0
-    spec = box3d((nel * px, nel * py, nel), nop, warp=warp, L=(L * px, L * py, L),
-                 periodic=(True, True, False) if periodic else (False, False, False))
+    if config == "c2":
+        spec = box3d((10, 10, 10), 4, warp=warp)
+    elif config == "c3":
+        spec = box2d((128, 32), 5, warp=warp, lo=(0.0, 0.0), hi=(25600.0, 6400.0))
+    elif config == "c4":
+        spec = box3d((64, 64, 24), 4, warp=warp, L=(L, L, 0.375 * L), periodic=(True, True, False))
+    else:
+        px, py = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[nranks]
+        spec = box3d((nel * px, nel * py, nel), nop, warp=warp, L=(L * px, L * py, L),
+                     periodic=(True, True, False) if periodic else (False, False, False))
     sem = sem_setup_rank(spec, rank, nranks)
+    neqs = spec.nsd + 2
     qn, qe = rtb_initial_state(sem.mesh, lpert, seed=1234)
-    conformity4ncf_q_rank(sem, qn, 5)                 # params_setup.jl:259-297 IC conditioning
-    conformity4ncf_q_rank(sem, qe, 5)
+    conformity4ncf_q_rank(sem, qn, neqs)              # params_setup.jl:259-297 IC conditioning
+    conformity4ncf_q_rank(sem, qe, neqs)
     return spec, sem, qn, qe
 
 
-def cpu_sample(nel, nop, lvisc, reps):
-    """Time the CPU oracle (port of the reference's rhs!) on one core on an nel^3 sample."""
-    from helpers import MU3, PHYS, box3d, euler_case
+CONFIGS = {
+    # name: (nsd, nop, AV viscous term, scaling, description)
+    "c5": (3, None, None, "weak", "synthetic weak-scaling mesh, BASELINE configs[4]"),
+    "c2": (3, 4, True, "strong", "3D rising thermal bubble, 10x10x10 elements, AV mu=125, BASELINE configs[1]"),
+    "c3": (2, 5, True, "strong", "2D density-current box, 128x32 elements, AV mu=125, BASELINE configs[2]"),
+    "c4": (3, 4, True, "strong", "3D ABL-style box, 64x64x24 elements, periodic x,y, AV mu=125, BASELINE configs[3]"),
+}
+CK_A1, CK_B1 = -567301805773.0 / 1357537059087.0, 5161836677717.0 / 13612068292357.0   # second CK2N54 stage (jx_bench_rhs fused stage)
+
+
+def cpu_sample(nel, nop, lvisc, reps, config="c5"):
+    """Time the CPU oracle (port of the reference's rhs!) plus the 2N low-storage stage update on ONE core: an nel^3-element
+    box of the same discretisation (c5), or the configuration's own mesh cut down to at most nel^nsd elements."""
+    from helpers import MU2, MU3, PHYS, box2d, box3d, euler_case
     from oracle import ref
-    spec = box3d((nel, nel, nel), nop, warp=0.05)
+    nsd = CONFIGS[config][0]
+    if nsd == 2:
+        spec = box2d((min(128, nel * 4), min(32, nel)), nop, warp=0.05, lo=(0.0, 0.0), hi=(25600.0, 6400.0))
+    else:
+        per = (True, True, False) if config == "c4" else (False, False, False)
+        spec = box3d((nel, nel, nel), nop, warp=0.05, periodic=per)
     sems, qns, qes, us = euler_case(spec, 1, lpert=False, condition=False)
-    prob = ref.RefProblem(sems[0], qes[0], eq_id=0, lpert=False, lsource=True, lvisc=lvisc, visc_coeff=MU3, phys=PHYS, pow_mode=0)
-    run = ref.RefRun([prob])
+    neqs = nsd + 2
+    prob = ref.RefProblem(sems[0], qes[0], eq_id=0, lpert=False, lsource=True, lvisc=lvisc, visc_coeff=MU3 if nsd == 3 else MU2,
+                          phys=PHYS, pow_mode=0)
+    m = sems[0].mesh
+    caches = ref.setup_assembler([m.ip2gip], [m.gip2owner]) if config == "c4" else None
+    run = ref.RefRun([prob], caches)
     dus = [np.zeros_like(us[0])]
+    tmp = np.zeros_like(us[0])
     run.rhs(dus, us, 0.0)
     t0 = time.perf_counter()
     for _ in range(reps):
         run.rhs(dus, us, 0.0)
+        tmp *= CK_A1                       # a dt = 0 stage: full stage traffic, state unchanged (as jx_bench_rhs)
+        tmp += 0.0 * dus[0]
+        us[0] += CK_B1 * tmp
     dt = (time.perf_counter() - t0) / reps
-    return sems[0].mesh.npoin * 5, dt
+    return m.npoin * neqs, dt
 
 
 def _cpu_worker(args):
@@ -147,8 +184,9 @@ def _cpu_worker(args):
 
 
 def run_reference(a):
-    """--impl reference: the reference's CPU rhs! (oracle port) on all host cores, one independent
-    element partition per core (its MPI layout without the negligible interface exchange)."""
+    """--impl reference: the reference's CPU rhs! (oracle port) + stage update on all host cores, one independent element
+    partition per core (its MPI layout without the negligible interface exchange).  Every partition (ref_nel^3 elements,
+    ~140 MB of metric terms at 24^3) exceeds the per-core share of the last-level cache."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -158,17 +196,18 @@ def run_reference(a):
     nel = a.ref_nel
     with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(max(a.warmup, 0) and 1):
-            pool.map(_cpu_worker, [(4, a.nop, a.visc, 1)] * cores)
+            pool.map(_cpu_worker, [(4, a.nop, a.visc, 1, a.config)] * cores)
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(nel, a.nop, a.visc, a.steps)] * cores)
+        res = pool.map(_cpu_worker, [(nel, a.nop, a.visc, a.steps, a.config)] * cores)
         wall = time.perf_counter() - t0
     dofs = sum(r[0] for r in res)
     t_step = max(r[1] for r in res)
     value = dofs / t_step / 1e9
-    sample = f"{cores} independent {nel}^3-element nop={a.nop} partitions, {a.steps} rhs! evaluations each"
+    sample = (f"{cores} independent {nel}^{CONFIGS[a.config][0]}-element nop={a.nop} partitions ({res[0][0]} DOF each), "
+              f"{a.steps} rhs! evaluations + stage updates each, one process per core")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "warmup": a.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": CONFIGS[a.config][3],
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "cpu_sample": sample, "wall_s": wall},
             "cpu_baseline": {"value": value, "unit": "GDOF/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -183,8 +222,8 @@ def build_oracle_only():
 
 def resolve_overlap(overlap, world, env):
     """--overlap -1 (auto): interface-first split with 4 SMs left to the exchange when there is one (N > 1), else off.
-    When the split is on, the exchange's NCCL send/recv kernels must fit on those SMs (one CTA per channel, one CTA
-    per SM), so the channel count is capped in ``env`` before any communicator exists."""
+    The NCCL channel cap that keeps the exchange kernels on those SMs is applied inside jx_init (ncclCommInitRankConfig);
+    the environment variables are set as well for NCCL builds that ignore the config fields."""
     if overlap < 0:
         overlap = 4 if world > 1 else 0
     if overlap > 0:
@@ -194,36 +233,50 @@ def resolve_overlap(overlap, world, env):
 
 
 def workload_name(a):
-    return (f"CompEuler theta 3D TOTAL {'AV mu=125' if a.visc else 'inviscid'} + gravity source, nop={a.nop}, "
-            f"{a.nel}^3 elements per GPU (synthetic weak-scaling mesh, BASELINE configs[4])")
+    nsd, _, _, _, desc = CONFIGS[a.config]
+    size = f"{a.nel}^3 elements per GPU" if a.config == "c5" else "whole mesh partitioned over the GPUs"
+    return (f"CompEuler theta {nsd}D TOTAL {'AV mu=125' if a.visc else 'inviscid'} + gravity source, nop={a.nop}, {size} ({desc})")
+
+
+def elem_kernel_name(ctx_variant, a):
+    if a.visc and ctx_variant == 9:
+        return "k_elem_team + k_visc_team (inviscid warp-team kernel followed by the AV viscous warp-team pass)"
+    return {9: "k_elem_team (fused flux + divergence per element pair; variant 9)",
+            8: "k_elem_team (variant 8)", 10: "k_elem_team2 (variant 10)", 11: "k_elem_team2 (variant 11)",
+            12: "k_elem_tri (three-role pencil kernel, nop 7)"}.get(
+        ctx_variant, "k_elem_node (generic fused flux + divergence%s, thread per node)" % (" + AV viscous term" if a.visc else ""))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default="c5", choices=sorted(CONFIGS))
     ap.add_argument("--nel", type=int, default=73)
     ap.add_argument("--nop", type=int, default=4)
     ap.add_argument("--visc", action="store_true")
     ap.add_argument("--pert", action="store_true")
     ap.add_argument("--dss-mode", type=int, default=int(os.environ.get("JX_DSS_MODE", "1")))
     ap.add_argument("--pow-mode", type=int, default=int(os.environ.get("JX_POW_MODE", "1")))
-    ap.add_argument("--elem-kernel", type=int, default=int(os.environ.get("JX_ELEM_KERNEL", "9")))
-    ap.add_argument("--graph", type=int, default=int(os.environ.get("JX_BENCH_GRAPH", "1")))
+    ap.add_argument("--elem-kernel", type=int, default=int(os.environ.get("JX_ELEM_KERNEL", "0")),
+                    help="JX_OPT_ELEM_KERNEL: 0 = JX_ELEM_AUTO (fastest exact-order kernel of the configuration), -1 generic, 8..12 a variant")
+    ap.add_argument("--graph", type=int, default=int(os.environ.get("JX_BENCH_GRAPH", "1")),
+                    help="1: the timed regions replay one captured evaluation as a CUDA graph (declared mode); 0: eager enqueue")
     ap.add_argument("--overlap", type=int, default=int(os.environ.get("JX_OVERLAP", "-1")),
                     help="JX_OPT_OVERLAP: interface groups first, exchange beside the interior launch; value = SMs left to the "
                          "exchange (0 = off; -1 = auto: 4 at N > 1, where there is an exchange to hide)")
-    ap.add_argument("--periodic", action="store_true", help="periodic x,y box (self-exchange of the twins; small meshes only)")
-    ap.add_argument("--ref-nel", type=int, default=12)
-    ap.add_argument("--cpu-nel", type=int, default=16)
+    ap.add_argument("--periodic", action="store_true", help="c5 only: periodic x,y box (self-exchange of the twins; small meshes only)")
+    ap.add_argument("--ref-nel", type=int, default=24)
+    ap.add_argument("--cpu-nel", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
-    if a.elem_kernel >= 1 and (a.visc or a.nop not in (2, 4)):
-        a.elem_kernel = 0        # the 3D fast paths are inviscid, nop <= 4; everything else runs the generic k_elem_node
+    nsd, cnop, cvisc, scaling, _ = CONFIGS[a.config]
+    if cnop is not None:
+        a.nop, a.visc = cnop, cvisc
     if a.impl == "reference":
         return run_reference(a)
     a.overlap = resolve_overlap(a.overlap, int(os.environ.get("WORLD_SIZE", "1")), os.environ)
@@ -232,7 +285,7 @@ def main():
     import torch.distributed as dist
     from jexpresso_b200 import capi
     from jexpresso_b200 import rhs as jrhs
-    from helpers import MU3
+    from helpers import MU2, MU3
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -252,18 +305,19 @@ def main():
         uid = box[0]
 
     t_setup = time.perf_counter()
-    spec, sem, qn, qe = build_problem(a.nel, a.nop, a.pert, rank, world, periodic=a.periodic)
-    neqs = 5
+    spec, sem, qn, qe = build_problem(a.nel, a.nop, a.pert, rank, world, periodic=a.periodic, config=a.config)
+    neqs = nsd + 2
     N = sem.mesh.npoin
-    inputs = {"SOL_VARS_TYPE": "PERT" if a.pert else "TOTAL", "lsource": True, "lvisc": a.visc, "mu": MU3, "dt": 0.1,
-              "ode_solver": "CarpenterKennedy2N54"}
+    inputs = {"SOL_VARS_TYPE": "PERT" if a.pert else "TOTAL", "lsource": True, "lvisc": a.visc, "mu": MU3 if nsd == 3 else MU2,
+              "dt": 0.1, "ode_solver": "CarpenterKennedy2N54"}
     params = jrhs.params_setup(sem, qe, inputs, device=local, rank=rank, nranks=world, nccl_uid=uid,
                                dss_mode=a.dss_mode, pow_mode=a.pow_mode, elem_kernel=a.elem_kernel, overlap=a.overlap)
     ctx = params.ctx
+    variant = ctx.kernel_variant()
     split = ctx.split_info()
     u0 = np.ascontiguousarray(qn[:, :neqs].reshape(-1, order="F"))
     ctx.set_state(u0)
-    # global unique nodes (weak scaling: shared interface nodes counted once)
+    # global unique nodes (shared interface nodes counted once)
     n_owned = int(np.count_nonzero(sem.mesh.gip2owner == rank)) if world > 1 else N
     setup_s = time.perf_counter() - t_setup
 
@@ -289,51 +343,43 @@ def main():
     total_dofs = sum_over_ranks(float(n_owned)) * neqs
 
     # ---- device-resident timing ---------------------------------------------------------------
-    # The timed region replays ONE captured RHS evaluation (all kernels and, at N > 1, the NCCL send/recv groups of
-    # the interface exchange) K times as a CUDA graph: the host's enqueue cost stays out of it.  If the capture is
-    # refused the same K evaluations are enqueued eagerly.  Per-phase times come from a second, eager pass of K
-    # evaluations with CUDA events around every phase (the element kernel's launch time for the roofline).
+    # ONE declared enqueue mode for every timed region: replay of one captured evaluation (all kernels and, at N > 1, the
+    # NCCL send/recv groups of the interface exchange) as a CUDA graph, or -- if --graph 0, or if the capture is refused on
+    # any rank -- eager enqueue.  Timed regions of exactly K evaluations each, CUDA events, barrier + sync on both sides,
+    # max over ranks:  (1) rhs! + M^-1 + 2N low-storage stage update = the headline (t_RHS includes the stage
+    # axpy);  (2) rhs! alone;  (3) rhs! alone, eager, with CUDA events around every phase (element-kernel launch time for the
+    # roofline; never the headline).
     graph = bool(a.graph)
     ctx.set_option(capi.JX_OPT_CUDA_GRAPH, 1 if graph else 0)
     try:
-        ctx.bench_rhs(a.warmup, fused_stage=False, phases=False)
+        ctx.bench_rhs(a.warmup, fused_stage=True, phases=False)
     except capi.JexError:
         graph = False
         ctx.set_option(capi.JX_OPT_CUDA_GRAPH, 0)
-        ctx.bench_rhs(a.warmup, fused_stage=False, phases=False)
-    flag = sum_over_ranks(0.0 if graph else 1.0)          # all ranks take the same path
-    if flag > 0 and graph:
+        ctx.bench_rhs(a.warmup, fused_stage=True, phases=False)
+    if sum_over_ranks(0.0 if graph else 1.0) > 0 and graph:   # all ranks take the same path
         graph = False
         ctx.set_option(capi.JX_OPT_CUDA_GRAPH, 0)
+    timed_mode = "graph" if graph else "eager"
     barrier()
     l0 = ctx.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, _ = ctx.bench_rhs(a.steps, fused_stage=False, phases=False)
+    ms_f, _ = ctx.bench_rhs(a.steps, fused_stage=True, phases=False)
     barrier()
     launches = ctx.launch_count() - l0
-    ms = max_over_ranks(ms)
-    ms_graph = ms
-    t_step = ms / a.steps * 1e-3
+    ms_f = max_over_ranks(ms_f)
+    t_step = ms_f / a.steps * 1e-3
     value = total_dofs / t_step / 1e9
+    ctx.bench_rhs(a.warmup, fused_stage=False, phases=False)
+    barrier()
+    ms_r, _ = ctx.bench_rhs(a.steps, fused_stage=False, phases=False)
+    barrier()
+    ms_r = max_over_ranks(ms_r)
     ctx.set_option(capi.JX_OPT_CUDA_GRAPH, 0)
     ms_eager, phases = ctx.bench_rhs(a.steps, fused_stage=False, phases=True)
     barrier()
-    clocks = sampler.stop() if sampler else None      # clocks sampled across both timed regions
+    clocks = sampler.stop() if sampler else None      # clocks sampled across the timed regions
     ms_eager = max_over_ranks(ms_eager)
-    # both regions time exactly K evaluations between barriers; the headline is the faster enqueue mode
-    # (the graph wins at N <= 2, eager enqueue at N = 8 where the replayed NCCL groups serialise more)
-    timed_mode = "graph" if graph else "eager"
-    if ms_eager < ms:
-        ms, timed_mode = ms_eager, "eager"
-        t_step = ms / a.steps * 1e-3
-        value = total_dofs / t_step / 1e9
-    # fused low-storage stage (RHS + M^-1 + RK update), reported beside the headline
-    ctx.set_option(capi.JX_OPT_CUDA_GRAPH, 1 if graph else 0)
-    ctx.bench_rhs(2, fused_stage=True, phases=False)
-    barrier()
-    ms_f, _ = ctx.bench_rhs(a.steps, fused_stage=True, phases=False)
-    ms_f = max_over_ranks(ms_f)
-    ctx.set_option(capi.JX_OPT_CUDA_GRAPH, 0)
 
     # ---- end to end through rhs!(du, u, params, t) with pinned host buffers ---------------------
     e2e = None
@@ -352,8 +398,21 @@ def main():
         barrier()
         t_e2e = max_over_ranks((time.perf_counter() - t0) / k_e2e)
         checksum = float(dn[:8].sum())
+        # achieved copy rates of this rank while every rank copies at once (what saturates at N = 8: see DESIGN.md section 6)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.set_state(un)
+        h2d_gbs = 3 * N * neqs * 8 / (time.perf_counter() - t0) / 1e9
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.get_state_into(dn)
+        d2h_gbs = 3 * N * neqs * 8 / (time.perf_counter() - t0) / 1e9
+        barrier()
         e2e = {"value": total_dofs / t_e2e / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": int(N * neqs * 8),
                "d2h_bytes_per_step": int(N * neqs * 8), "ms_per_step": t_e2e * 1e3, "checksum": checksum,
+               "h2d_gbs_this_rank": h2d_gbs, "d2h_gbs_this_rank": d2h_gbs,
                "api": "jexpresso_b200.capi.Context.rhs == jx_rhs(ctx,t,u_host,du_host,NULL)"}
 
     def shutdown():
@@ -373,48 +432,53 @@ def main():
     peak, peak_src = peaks()
     traffic = None   # dram bytes of one element-kernel launch from the committed ncu --set full capture of this workload
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01g_elem_traffic.json")))
-        if (tr["elem_kernel"], tr["nel"], tr["nop"], tr["pert"]) == (a.elem_kernel, a.nel, a.nop, bool(a.pert)) and not a.visc:
-            traffic = tr["dram_bytes_per_launch"]
+        for tr in json.load(open(os.path.join(ROOT, "profiles", "elem_traffic.json"))):
+            if (tr["config"], tr["elem_kernel"], tr["nel"], tr["nop"], tr["pert"], tr["visc"]) == \
+                    (a.config, variant, a.nel, a.nop, bool(a.pert), bool(a.visc)):
+                traffic = tr["dram_bytes_per_launch"]
     except Exception:
         pass
     elem_ms = phases[1] / a.steps
-    elem_bytes = elem_kernel_bytes_per_node(a.nop, a.pert) * N
+    r_el = ((a.nop + 1) / a.nop) ** nsd
+    elem_bytes = (8 * neqs + r_el * (8 * (nsd * nsd + 1) + 8) + (8 * (neqs + 1) if a.pert else 0)) * N
     achieved = elem_bytes / (elem_ms * 1e-3) / 1e9 if elem_ms > 0 else 0.0
-    rhs_bytes = algorithmic_bytes_per_node(a.nop, a.pert) * N
-    rhs_gbs = rhs_bytes / t_step / 1e9 * (1.0 if world == 1 else 1.0)
+    rhs_bytes_node = 8 * neqs * 2 + 8 + r_el * (8 * (nsd * nsd + 1) + 8) + (8 * (neqs + 1) if a.pert else 0)
+    fused_bytes = (rhs_bytes_node + 8 * neqs * 2) * N
     line = {
         "metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(a), "nodes_per_gpu": N, "elements_per_gpu": sem.mesh.nelem, "neqs": neqs,
-                   "l2": "inputs (3.9 GB metric records + 1 GB state per GPU) >> 126 MB L2; no flush needed",
-                   "dss_mode": a.dss_mode, "pow_mode": a.pow_mode, "elem_kernel": a.elem_kernel, "setup_s": round(setup_s, 1),
+        "value_rhs_only": total_dofs / (ms_r / a.steps * 1e-3) / 1e9,
+        "config": {"workload": workload_name(a), "config": a.config, "nodes_per_gpu": N, "elements_per_gpu": sem.mesh.nelem, "neqs": neqs,
+                   "l2": "inputs (metric records + state per GPU) >> 126 MB L2 at c5 / c4 sizes; no flush needed"
+                         if N * neqs * 8 > 2.6e8 else "inputs fit the 126 MB L2: small-mesh configuration, launch bound",
+                   "dss_mode": a.dss_mode, "pow_mode": a.pow_mode, "elem_kernel": variant, "setup_s": round(setup_s, 1),
                    "overlap": {"sms_left_to_exchange": a.overlap, "interface_groups": split[0], "interior_groups": split[1]},
-                   "periodic_xy": bool(a.periodic),
+                   "periodic_xy": bool(a.periodic) or a.config == "c4",
                    "phase_ms_per_step": {k: round(v / a.steps, 4) for k, v in
                                          zip(("bc", "elem", "dss", "halo", "update", "aux"), phases[:6])},
-                   "timing": "two timed regions of K RHS evaluations each (CUDA events, barrier + sync on both sides, max over ranks): "
-                             "(a) CUDA graph replay of one captured evaluation incl. the NCCL groups, (b) eager enqueue with CUDA "
-                             "events around every phase (source of phase_ms_per_step); headline = " + timed_mode,
-                   "graph_ms_per_step": (ms_graph / a.steps) if graph else None,
-                   "eager_ms_per_step": ms_eager / a.steps,
-                   "fused_stage_ms_per_step": ms_f / a.steps,
-                   "fused_stage_gdofs": total_dofs / (ms_f / a.steps * 1e-3) / 1e9},
-        "roofline": {"bound": "hbm", "kernel": ("k_elem_team (fused flux + divergence per element group; variant %d)" % a.elem_kernel) if a.elem_kernel >= 8
-                     else ("k_elem_node (generic fused flux + divergence%s, thread per node)" % (" + AV viscous term" if a.visc else "")) if a.elem_kernel <= 0
-                     else "element kernel variant %d" % a.elem_kernel, "achieved": achieved,
+                   "timing": "value = K evaluations of rhs! + M^-1 + 2N low-storage stage update (SURVEY 8d t_RHS), value_rhs_only = K "
+                             "evaluations of rhs! alone; both in ONE declared enqueue mode (" + timed_mode + "), CUDA events, barrier + sync "
+                             "on both sides, max over ranks; phase_ms_per_step from a third, eager region with events around every phase",
+                   "enqueue_mode": timed_mode,
+                   "rhs_only_ms_per_step": ms_r / a.steps,
+                   "rhs_only_eager_with_phase_events_ms_per_step": ms_eager / a.steps},
+        "roofline": {"bound": "hbm", "kernel": elem_kernel_name(variant, a), "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": elem_bytes, "launch_ms": elem_ms,
-                     "whole_rhs": {"achieved": rhs_gbs, "frac": rhs_gbs / peak, "bytes_per_node": algorithmic_bytes_per_node(a.nop, a.pert)}},
+                     "whole_step": {"achieved": fused_bytes / t_step / 1e9, "frac": fused_bytes / t_step / 1e9 / peak,
+                                    "bytes_per_node": fused_bytes / N}},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
     }
     if world == 1 and not a.no_cpu:
         build_oracle_only()
         t0 = time.perf_counter()
-        dofs, dt = cpu_sample(a.cpu_nel, a.nop, a.visc, 3)
+        reps = 5
+        dofs, dt = cpu_sample(a.cpu_nel, a.nop, a.visc, reps, a.config)
         line["cpu_baseline"] = {"value": dofs / dt / 1e9, "unit": "GDOF/s", "cores": 1, "kind": "port",
-                                "sample": f"oracle/jexref.c rhs! on a {a.cpu_nel}^3-element nop={a.nop} box, 3 evaluations, 1 thread",
+                                "sample": f"oracle/jexref.c rhs! + stage update on {dofs} DOF of the same discretisation "
+                                          f"({a.cpu_nel}^{nsd} elements, nop={a.nop}, working set beyond the last-level cache), "
+                                          f"{reps} evaluations, 1 thread",
                                 "wall_s": round(time.perf_counter() - t0, 1)}
     print(json.dumps(line))
     shutdown()

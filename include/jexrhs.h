@@ -62,8 +62,9 @@ typedef struct jx_ctx jx_ctx;
                                   to the oracle's jx_pow */
 #define JX_OPT_ELEM_KERNEL 3   /* element-kernel variant: JX_ELEM_AUTO (default) picks the fastest exact-order kernel that
                                   exists for the configuration (3D inviscid nop 2/4: the warp-team kernel, else the generic
-                                  one); JX_ELEM_GENERIC forces the generic thread-per-node kernel; 1..9 name a variant
-                                  (DESIGN.md section 4).  All exact-order variants give bit-identical results. */
+                                  one); JX_ELEM_GENERIC forces the generic thread-per-node kernel; 8 / 9 name the warp-team kernel
+                                  (one / two plane warps), 10 / 11 its TMA-fed successor k_elem_team2.
+                                  All variants keep the reference's order of every sum: bit-identical results. */
 #define JX_ELEM_AUTO 0
 #define JX_ELEM_GENERIC (-1)
 #define JX_OPT_CUDA_GRAPH 4    /* 1: jx_bench_rhs captures one RHS evaluation, and jx_step(CK2N54) one whole step (five stages:
@@ -76,6 +77,10 @@ typedef struct jx_ctx jx_ctx;
 /* replaces: MPI.Init / get_mpi_comm (src/run.jl:74-88).  nccl_uid: 128-byte ncclUniqueId shared
  * by all ranks (see jx_nccl_unique_id) or NULL when nranks == 1. */
 int jx_init(int device, int rank, int nranks, const void *nccl_uid, jx_ctx **out);
+/* jx_init with the communicator capped to nccl_max_ctas CTAs (ncclCommInitRankConfig, maxCTAs): the NCCL send/recv kernels of
+ * the interface exchange then fit on the SMs JX_OPT_OVERLAP = nccl_max_ctas leaves free of the interior element launch, whatever
+ * the host process's environment says.  0 = no cap (= jx_init). */
+int jx_init_ex(int device, int rank, int nranks, const void *nccl_uid, int nccl_max_ctas, jx_ctx **out);
 int jx_nccl_unique_id(void *uid128);
 void jx_destroy(jx_ctx *);
 int jx_last_error(jx_ctx *, char *buf, int len);
@@ -123,6 +128,14 @@ int jx_get_du(jx_ctx *, double *du);
  * u_back_host != NULL: download the state after the Dirichlet projection (rhs! mutates u, BCs.jl:651).
  * All NULL => fully device resident (state set by jx_set_state / advanced by jx_step). */
 int jx_rhs(jx_ctx *, double t, const double *u_host, double *du_host, double *u_back_host);
+
+/* rhs!(du,u,params,time) on DEVICE arrays the caller owns (a CuArray state under OrdinaryDiffEq: no PCIe copy): u_dev and
+ * du_dev are Float64[npoin*neqs] in the same flat layout, on the context's device; u_dev is projected in place (rhs! mutates
+ * u), du_dev receives the mass-scaled right-hand side.  Returns after the context's stream has drained. */
+int jx_rhs_dev(jx_ctx *, double t, double *u_dev, double *du_dev);
+
+/* element-kernel variant in use after JX_ELEM_AUTO resolution (0 = generic k_elem_node); negative JX_E* before jx_set_problem */
+int jx_kernel_variant(jx_ctx *);
 
 /* replaces: OrdinaryDiffEq perform_step! for the fixed-step explicit schemes the decks use; all stages on the
  * device, M^-1 fused with the stage update, no host round trip.  dt is used as given (the Julia side passes

@@ -47,6 +47,9 @@ def lib():
     L = ctypes.CDLL(LIB_PATH)
     vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
     L.jx_init.argtypes = [i32, i32, i32, vp, ctypes.POINTER(vp)]
+    L.jx_init_ex.argtypes = [i32, i32, i32, vp, i32, ctypes.POINTER(vp)]
+    L.jx_rhs_dev.argtypes = [vp, dbl, vp, vp]
+    L.jx_kernel_variant.argtypes = [vp]
     L.jx_nccl_unique_id.argtypes = [vp]
     L.jx_destroy.argtypes = [vp]
     L.jx_destroy.restype = None
@@ -99,10 +102,10 @@ def nccl_unique_id() -> bytes:
 class Context:
     """Thin owner of one ``jx_ctx`` (one per rank / GPU)."""
 
-    def __init__(self, device=0, rank=0, nranks=1, nccl_uid: bytes | None = None):
+    def __init__(self, device=0, rank=0, nranks=1, nccl_uid: bytes | None = None, nccl_max_ctas=0):
         self._h = ctypes.c_void_p()
         uid = ctypes.create_string_buffer(nccl_uid, 128) if nccl_uid is not None else None
-        rc = lib().jx_init(device, rank, nranks, uid, ctypes.byref(self._h))
+        rc = lib().jx_init_ex(device, rank, nranks, uid, int(nccl_max_ctas), ctypes.byref(self._h))
         if rc:
             self._h = ctypes.c_void_p()
             raise JexError(rc, "jx_init failed (no CUDA device / bad arguments / NCCL)")
@@ -179,6 +182,20 @@ class Context:
         u = np.empty(self.npoin * self.neqs)
         self._ck(lib().jx_get_state(self._h, _ptr(u)))
         return u
+
+    def get_state_into(self, u):
+        assert u.dtype == np.float64 and u.flags.c_contiguous and u.size == self.npoin * self.neqs
+        self._ck(lib().jx_get_state(self._h, _ptr(u)))
+
+    def kernel_variant(self):
+        v = lib().jx_kernel_variant(self._h)
+        if v < 0:
+            raise JexError(v, "jx_kernel_variant before jx_set_problem")
+        return v
+
+    def rhs_dev(self, t, u_ptr, du_ptr):
+        """rhs!(du,u,params,t) on device arrays the caller owns (raw device pointers, e.g. torch.Tensor.data_ptr())."""
+        self._ck(lib().jx_rhs_dev(self._h, float(t), ctypes.c_void_p(int(u_ptr)), ctypes.c_void_p(int(du_ptr))))
 
     def get_du(self):
         du = np.empty(self.npoin * self.neqs)

@@ -28,6 +28,7 @@ struct NcclApi {
     void *h = nullptr;
     int (*GetUniqueId)(NcclUid *) = nullptr;
     int (*CommInitRank)(ncclComm_t *, int, NcclUid, int) = nullptr;
+    int (*CommInitRankConfig)(ncclComm_t *, int, NcclUid, int, void *) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -37,6 +38,16 @@ struct NcclApi {
     bool ok = false;
 };
 constexpr int kNcclFloat64 = 8;   // ncclFloat64 / ncclDouble
+// ncclConfig_t as of NCCL 2.18 (nccl.h: size, magic, version, then the user fields); newer libraries accept an older,
+// shorter struct by its size/version and default the fields it lacks.
+struct NcclConfig218 {
+    size_t size;
+    unsigned int magic, version;
+    int blocking, cgaClusterSize, minCTAs, maxCTAs;
+    const char *netName;
+    int splitShare;
+};
+constexpr int kNcclUndefInt = (-2147483647 - 1);
 
 NcclApi &nccl() {
     static NcclApi api;
@@ -53,6 +64,7 @@ NcclApi &nccl() {
 #define JX_SYM(field, sym) *(void **)(&api.field) = dlsym(api.h, sym)
     JX_SYM(GetUniqueId, "ncclGetUniqueId");
     JX_SYM(CommInitRank, "ncclCommInitRank");
+    JX_SYM(CommInitRankConfig, "ncclCommInitRankConfig");
     JX_SYM(CommDestroy, "ncclCommDestroy");
     JX_SYM(Send, "ncclSend");
     JX_SYM(Recv, "ncclRecv");
@@ -85,6 +97,7 @@ struct jx_ctx {
     ncclComm_t comm = nullptr;
     std::string err;
     int num_sms = 148;
+    int nccl_max_ctas = 0;           // CTA cap the communicator was created with (0: none)
     int64_t launches = 0;
 
     // problem (jx_set_problem)
@@ -107,6 +120,7 @@ struct jx_ctx {
     size_t aux_doubles = 0;
     double row_runs_per_elem = 0.0;  // k_elem_team2: bulk copies per element after merging consecutive node ids
     char *rec = nullptr;
+    char *rec_visc = nullptr;        // pair records of the viscous pass (k_visc_team), lvisc only
     int64_t *n2e_ptr = nullptr;
     uint32_t *n2e_idx = nullptr;
     double dpsi[64] = {0};
@@ -221,7 +235,7 @@ void free_split(jx_ctx *c) {
 void free_mesh(jx_ctx *c) {
     free_split(c);
     dfree(c->u); dfree(c->du); dfree(c->tmp); dfree(c->qe); dfree(c->Minv); dfree(c->coords);
-    dfree(c->rhs_el); dfree(c->rhs_el_visc); dfree(c->aux); c->aux_doubles = 0; dfree(c->rec); dfree(c->n2e_ptr); dfree(c->n2e_idx);
+    dfree(c->rhs_el); dfree(c->rhs_el_visc); dfree(c->aux); c->aux_doubles = 0; dfree(c->rec); dfree(c->rec_visc); dfree(c->n2e_ptr); dfree(c->n2e_idx);
     for (auto &p : c->ss) dfree(p);
     c->have_mesh = false;
     c->rec_layout = -1;
@@ -249,7 +263,7 @@ int select_kernels(jx_ctx *c) {
     if (c->elem_variant == JX_ELEM_AUTO) {
         // fastest exact-order kernel that exists for this configuration: the warp-team kernels (bit-identical to the
         // generic one), else the generic thread-per-node kernel.  Resident records pin the choice to their layout.
-        const int order[] = {10, 9, 8, 0};
+        const int order[] = {12, 9, 8, 0};   // 12: nop 7, 9/8: nop 4/2 (10/11 = k_elem_team2, opt-in: profiles/r02b)
         for (int v : order) {
             ks = lookup(v);
             if (ks && (!c->have_mesh || ks->rec_layout == c->rec_layout)) break;
@@ -266,6 +280,7 @@ int select_kernels(jx_ctx *c) {
         return fail(c, JX_ESTATE, "kernel variant %d reads element-record layout %d, the resident records have layout %d: "
                     "set JX_OPT_ELEM_KERNEL before jx_upload_mesh", ks->variant, ks->rec_layout, c->rec_layout);
     CK(ks->prepare());
+    if (ks->visc_prepare) CK(ks->visc_prepare());
     c->ks = ks;
     return JX_OK;
 }
@@ -287,6 +302,10 @@ extern "C" int jx_nccl_unique_id(void *uid128) {
 }
 
 extern "C" int jx_init(int device, int rank, int nranks, const void *nccl_uid, jx_ctx **out) {
+    return jx_init_ex(device, rank, nranks, nccl_uid, 0, out);
+}
+
+extern "C" int jx_init_ex(int device, int rank, int nranks, const void *nccl_uid, int nccl_max_ctas, jx_ctx **out) {
     if (!out) return JX_EINVAL;
     *out = nullptr;
     int ndev = 0;
@@ -305,7 +324,19 @@ extern "C" int jx_init(int device, int rank, int nranks, const void *nccl_uid, j
         if (!nccl_uid || !nccl().ok) { jx_destroy(c); return JX_ENCCL; }
         NcclUid id;
         memcpy(&id, nccl_uid, 128);
-        if (nccl().CommInitRank(&c->comm, nranks, id, rank) != 0) { jx_destroy(c); return JX_ENCCL; }
+        // The interface-first overlap (JX_OPT_OVERLAP) leaves nccl_max_ctas SMs free of the interior launch; the exchange's
+        // send/recv kernels take one CTA per channel, so the communicator is created with that many CTAs at most.
+        int rcn = -1;
+        if (nccl_max_ctas > 0 && nccl().CommInitRankConfig) {
+            NcclConfig218 cfg;
+            cfg.size = sizeof(NcclConfig218); cfg.magic = 0xcafebeef; cfg.version = 21803;
+            cfg.blocking = kNcclUndefInt; cfg.cgaClusterSize = kNcclUndefInt; cfg.minCTAs = 1; cfg.maxCTAs = nccl_max_ctas;
+            cfg.netName = nullptr; cfg.splitShare = kNcclUndefInt;
+            rcn = nccl().CommInitRankConfig(&c->comm, nranks, id, rank, &cfg);
+            if (rcn != 0) c->comm = nullptr;
+        }
+        if (rcn != 0 && nccl().CommInitRank(&c->comm, nranks, id, rank) != 0) { jx_destroy(c); return JX_ENCCL; }
+        c->nccl_max_ctas = rcn == 0 ? nccl_max_ctas : 0;
     }
     *out = c;
     return JX_OK;
@@ -440,9 +471,10 @@ int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, co
     const int np = c->np, q = c->neqs;
     const int64_t total = E * np;
     const size_t nq = (size_t)N * q;
-    const bool grouped = c->ks->rec_layout >= 4;      // group records (4: k_elem_gpencil, 5: k_elem_team)
+    const bool tri = c->ks->rec_layout == 7;          // per-element pencil-stream records of k_elem_tri
+    const bool grouped = c->ks->rec_layout == 5 || c->ks->rec_layout == 6;   // element-group records of the team kernels (6: + row-run tables)
     const int64_t ngroups = grouped ? (E + c->ks->elems_per_block - 1) / c->ks->elems_per_block : 0;
-    const size_t rec_total = grouped ? (size_t)ngroups * c->ks->group_bytes : (size_t)E * c->rec_bytes;
+    const size_t rec_total = grouped ? (size_t)ngroups * c->ks->group_bytes : (tri ? (size_t)E * c->ks->group_bytes : (size_t)E * c->rec_bytes);
     int rc;
     if ((rc = dalloc(c, &c->u, nq)) || (rc = dalloc(c, &c->du, nq)) || (rc = dalloc(c, &c->tmp, nq)) ||
         (rc = dalloc(c, &c->Minv, (size_t)N)) || (rc = dalloc(c, &c->qe, (size_t)N * (q + 1))) ||
@@ -499,28 +531,63 @@ int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, co
     RetileArgs ra;
     ra.omega = d_omega; ra.connijk = d_conn; ra.rec = c->rec; ra.nelem = E; ra.nsd = c->nsd; ra.ngl = c->ngl; ra.np = np;
     ra.nmet = c->nmet; ra.npp = (np + 3) / 4 * 4; ra.rec_bytes = c->rec_bytes; ra.src = nullptr;
-    ra.layout = c->ks->rec_layout;
-    if (total > 0 && grouped) {
+    if (total > 0 && tri) {
+        const KernelSet *ks = c->ks;
+        TriRetileArgs ta;
+        ta.src = nullptr; ta.omega = d_omega; ta.Minv = c->Minv; ta.connijk = d_conn; ta.rec = c->rec; ta.nelem = E; ta.ngl = c->ngl;
+        ta.rec_bytes = ks->group_bytes; ta.zid_off = ks->zid_off; ta.fid_off = ks->fid_off;
+        CKC(cudaMemsetAsync(c->rec, 0, rec_total, c->stream));
+        ta.slot = -1;
+        k_retile_tri<<<nblk(total, 256), 256, 0, c->stream>>>(ta);
+        for (int m = 0; m < c->nmet; ++m) {
+            if (metrics && !metrics[m]) { cleanup(); return fail(c, JX_EINVAL, "metric array %d is null", m); }
+            CKC(stage_metric(m));
+            ta.src = d_stage; ta.slot = m;
+            k_retile_tri<<<nblk(total, 256), 256, 0, c->stream>>>(ta);
+            CKC(cudaStreamSynchronize(c->stream));
+        }
+        ta.slot = -2;
+        k_retile_tri<<<nblk(total, 256), 256, 0, c->stream>>>(ta);
+        c->launches += c->nmet + 2;
+    } else if (total > 0 && grouped) {
         const KernelSet *ks = c->ks;
         GroupRetileArgs ga;
         ga.src = nullptr; ga.omega = d_omega; ga.Minv = c->Minv; ga.connijk = d_conn; ga.rec = c->rec; ga.nelem = E;
-        ga.ngl = c->ngl; ga.epb = ks->elems_per_block; ga.nt = ks->group_nt; ga.group_bytes = ks->group_bytes;
-        ga.zid_off = ks->zid_off; ga.fid_off = ks->fid_off; ga.layout = ks->rec_layout; ga.z_off = ks->z_off;
-        for (int ps = 0; ps < 3; ++ps)
-            for (int d = 0; d < 3; ++d) ga.mult[ps][d] = ks->group_mult[ps][d];
+        ga.ngl = c->ngl; ga.epb = ks->elems_per_block; ga.group_bytes = ks->group_bytes;
+        ga.zid_off = ks->zid_off; ga.fid_off = ks->fid_off; ga.z_off = ks->z_off;
         CKC(cudaMemsetAsync(c->rec, 0, rec_total, c->stream));
         ga.slot = -1;
         k_retile_group<<<nblk(total, 256), 256, 0, c->stream>>>(ga);
+        ViscRetileArgs vr;
+        const bool with_visc = ks->launch_visc != nullptr;
+        if (with_visc) {                               // records of the viscous pass, built from the same staged arrays
+            const size_t vbytes = (size_t)ngroups * ks->visc_group_bytes;
+            if ((rc = dalloc(c, &c->rec_visc, vbytes))) { cleanup(); return rc; }
+            CKC(cudaMemsetAsync(c->rec_visc, 0, vbytes, c->stream));
+            vr.src = nullptr; vr.omega = d_omega; vr.Minv = c->Minv; vr.connijk = d_conn; vr.rec = c->rec_visc; vr.nelem = E;
+            vr.ngl = c->ngl; vr.epb = ks->elems_per_block; vr.group_bytes = ks->visc_group_bytes; vr.zslot_bytes = ks->visc_zslot_bytes;
+            vr.zid_off = ks->visc_zid_off; vr.fid_off = ks->visc_fid_off;
+            vr.slot = -1;
+            k_retile_visc<<<nblk(total, 256), 256, 0, c->stream>>>(vr);
+        }
         for (int m = 0; m < c->nmet; ++m) {
             if (metrics && !metrics[m]) { cleanup(); return fail(c, JX_EINVAL, "metric array %d is null", m); }
             CKC(stage_metric(m));
             ga.src = d_stage; ga.slot = m;
             k_retile_group<<<nblk(total, 256), 256, 0, c->stream>>>(ga);
+            if (with_visc) {
+                vr.src = d_stage; vr.slot = m;
+                k_retile_visc<<<nblk(total, 256), 256, 0, c->stream>>>(vr);
+            }
             CKC(cudaStreamSynchronize(c->stream));
         }
         ga.slot = -2;                                  // -(omega*J*Minv): needs the ids, omega*J and Minv in place
         k_retile_group<<<nblk(total, 256), 256, 0, c->stream>>>(ga);
-        c->launches += c->nmet + 2;
+        if (with_visc) {
+            vr.slot = -2;
+            k_retile_visc<<<nblk(total, 256), 256, 0, c->stream>>>(vr);
+        }
+        c->launches += (c->nmet + 2) * (with_visc ? 2 : 1);
         if (ks->maxrun > 0) {
             CKC(cudaStreamSynchronize(c->stream));
             const int rr = build_row_runs(c, connijk);
@@ -864,7 +931,10 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     if (!atomics && (!c->rhs_el || (c->lvisc && !c->rhs_el_visc))) {
         int rc;
         if (!c->rhs_el && (rc = dalloc(c, &c->rhs_el, (size_t)E * c->np * q))) return rc;
-        if (c->lvisc && !c->rhs_el_visc && (rc = dalloc(c, &c->rhs_el_visc, (size_t)E * c->np * q))) return rc;
+        if (c->lvisc && !c->rhs_el_visc) {
+            if ((rc = dalloc(c, &c->rhs_el_visc, (size_t)E * c->np * q))) return rc;
+            CK(cudaMemsetAsync(c->rhs_el_visc, 0, (size_t)E * c->np * q * 8, s));   // equations with mu = 0 are never written by k_visc_team
+        }
     }
     ElemArgs ea;
     ea.u = u; ea.qe = c->qe; ea.rec = c->rec; ea.rhs_el = c->rhs_el; ea.rhs_el_visc = c->rhs_el_visc; ea.du = du;
@@ -947,6 +1017,18 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
         const int grid = (int)std::min<int64_t>(ngroups, (int64_t)c->num_sms * per_sm);
         ks->launch_elem(ea, grid, s);                                    // rhs.jl:611, 659
         c->launches++;
+        if (c->lvisc && ks->launch_visc) {                               // AV viscous term as a pass of its own, rhs.jl:659-672
+            ViscArgs va;
+            va.rec = c->rec_visc; va.out_el = c->rhs_el_visc; va.nv = 0;
+            for (int e = 0; e < q && e < 8; ++e)
+                if (c->visc[e] != 0.0) va.ve[va.nv++] = e;
+            for (int i = va.nv; i < 8; ++i) va.ve[i] = 0;
+            if (va.nv > 0) {
+                const int vper = std::max(1, ks->visc_max_blocks());
+                ks->launch_visc(ea, va, (int)std::min<int64_t>(ngroups, (int64_t)c->num_sms * vper), s);
+                c->launches++;
+            }
+        }
     }
     if (!atomics) {
         PhaseScope ps(c, PH_DSS);
@@ -1026,6 +1108,32 @@ extern "C" int jx_rhs(jx_ctx *c, double t, const double *u_host, double *du_host
         CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     }
     return JX_OK;
+}
+
+extern "C" int jx_rhs_dev(jx_ctx *c, double t, double *u_dev, double *du_dev) {
+    (void)t;
+    if (!c || !u_dev || !du_dev) return JX_EINVAL;
+    if (!c->have_mesh) return fail(c, JX_ESTATE, "jx_rhs_dev before jx_upload_mesh");
+    cudaSetDevice(c->device);
+    cudaPointerAttributes pa, pb;
+    if (cudaPointerGetAttributes(&pa, u_dev) != cudaSuccess || cudaPointerGetAttributes(&pb, du_dev) != cudaSuccess ||
+        pa.type != cudaMemoryTypeDevice || pb.type != cudaMemoryTypeDevice || pa.device != c->device || pb.device != c->device) {
+        cudaGetLastError();
+        return fail(c, JX_EINVAL, "jx_rhs_dev: u and du must be device memory of device %d", c->device);
+    }
+    CK(cudaEventRecord(c->ev0, c->stream));
+    StageUpdate upd;
+    int rc = rhs_core(c, u_dev, du_dev, upd);     // the Dirichlet projection writes u_dev in place, like rhs! does with u
+    if (rc) return rc;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    return JX_OK;
+}
+
+extern "C" int jx_kernel_variant(jx_ctx *c) {
+    if (!c || !c->ks) return JX_ESTATE;
+    return c->ks->variant;
 }
 
 extern "C" int jx_step(jx_ctx *c, int scheme, double t, double dt, int nsteps) {

@@ -27,10 +27,15 @@ struct KernelSet {
     void (*launch_image)(const ImageArgs &, int grid, cudaStream_t) = nullptr;
     int img_rowd = 0;
     int wpos_off = 0, runi_off = 0, runr_off = 0, runl_off = 0, nrun_off = 0, maxrun = 0;   // row-run tables of the pair records
-    // rec_layout 4 (group records of k_elem_gpencil): bytes per group, lane columns, id offsets, lane encoders
+    // AV viscous term as a pass of its own (k_visc_team) behind an inviscid element kernel: its launcher and the layout of
+    // its pair records (nullptr: the element kernel itself carries the viscous pass, or lvisc = 0)
+    void (*launch_visc)(const ElemArgs &, const ViscArgs &, int grid, cudaStream_t) = nullptr;
+    int (*visc_max_blocks)() = nullptr;
+    cudaError_t (*visc_prepare)() = nullptr;
+    int visc_group_bytes = 0, visc_zslot_bytes = 0, visc_zid_off = 0, visc_fid_off = 0;
+    // rec_layout 5 (element-group records of the team kernels): bytes per group and stream / id offsets
     int group_bytes = 0, group_nt = 0, zid_off = 0, fid_off = 0, z_off = 0;
-    int group_mult[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // [pass][digit]: lane = s*m0 + c0*m1 + c1*m2
-    int has_dyn = 0;                                            // launch_elem honours ElemArgs::glist/gctr (interface-first split)
+ int has_dyn = 0;                                            // launch_elem honours ElemArgs::glist/gctr (interface-first split)
 };
 
 // each instantiation unit exports one lookup; returns nullptr if it does not hold the combination

@@ -73,25 +73,7 @@ struct RetileArgs {
     int64_t nelem;
     int nsd, ngl, np, nmet, npp, rec_bytes;
     int slot;                 // metric slot; nmet-1 = Je (stored as ωJac); -1 = connectivity
-    int layout;               // 0: met[slot][node]; 1: pencil streams (3D, see k_elem_pencil)
 };
-
-// Record layout 1 (3D, pencil kernel): the metric doubles of one element are stored in the order the
-// pencil kernel's threads consume them, so that every load instruction of a warp is one contiguous run.
-// Thread c in [0,n^2) owns the xi-pencil (j,k)=(c%n,c/n), the eta-pencil (i,k)=(c%n,c/n) and the
-// zeta-pencil (i,j)=(c%n,c/n); stream s of thread c sits at rec[s*n^2 + c]:
-//   s = q*n + m        (q=0..2)  d(xi)/d(x,y,z)   at node m of the xi-pencil
-//   s = 3n + q*n + m             d(eta)/d(x,y,z)  at node m of the eta-pencil
-//   s = 6n + q*n + m             d(zeta)/d(x,y,z) at node m of the zeta-pencil
-//   s = 9n + m                   ωJac             at node m of the zeta-pencil
-__host__ __device__ inline int pencil_stream_index(int n, int slot, int l) {
-    const int i = l % n, j = (l / n) % n, k = l / (n * n);
-    const int nc = n * n;
-    if (slot < 3) return (slot * n + i) * nc + (j + n * k);
-    if (slot < 6) return (3 * n + (slot - 3) * n + j) * nc + (i + n * k);
-    if (slot < 9) return (6 * n + (slot - 6) * n + k) * nc + (i + n * j);
-    return (9 * n + k) * nc + (i + n * j);
-}
 
 // element-fastest Julia arrays [E, n, n, n] -> per-element records; thread = (element, local node)
 static __global__ void k_retile(RetileArgs a) {
@@ -109,7 +91,7 @@ static __global__ void k_retile(RetileArgs a) {
         if (l == 0)
             for (int p = a.np; p < a.npp; ++p) rc[p] = 0;
     } else if (a.slot < a.nmet - 1) {
-        rm[a.layout == 1 ? pencil_stream_index(n, a.slot, l) : a.slot * a.np + l] = a.src[src];
+        rm[a.slot * a.np + l] = a.src[src];
     } else {
         const double Je = a.src[src];
         double wJ;
@@ -121,7 +103,7 @@ static __global__ void k_retile(RetileArgs a) {
             const int i = l % n, j = l / n;
             wJ = a.omega[i] * a.omega[j] * Je;               // rhs.jl:1515-1516
         }
-        rm[a.layout == 1 ? pencil_stream_index(n, a.nmet - 1, l) : (a.nmet - 1) * a.np + l] = wJ;
+        rm[(a.nmet - 1) * a.np + l] = wJ;
     }
 }
 
@@ -509,214 +491,13 @@ k_elem_node(const __grid_constant__ ElemArgs a) {
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Fused per-element kernel, variant "pencil" (3D, inviscid): the same arithmetic as k_elem_node,
-// re-tiled for the measured B200 limits.  A warp-wide LDS.64 costs 2 cycles (256 B through the
-// 128 B/clk shared-memory return path, broadcast or not -- scripts/micro/micro.cu) against 0.5 cycle
-// for a warp-wide DFMA, so the one-thread-per-node form (one shared load per FMA) is bound by shared
-// memory, not by FP64 or HBM (profiles/r01a).  Here every derivative direction is computed by the
-// thread that owns the whole LGL line ("pencil") in that direction: n loads feed n*n FMAs, and the
-// dψ entries are compile-time constant-bank operands.  Thread c of an element owns
-//     xi-pencil (j,k)=(c%n,c/n)   eta-pencil (i,k)=(c%n,c/n)   zeta-pencil (i,j)=(c%n,c/n)
-// and keeps the three metric terms of each of its pencils in registers for all equations (record
-// layout 1, pencil_stream_index).  Per equation:
-//     xi pass   : a_F = dF/dξ·ξx, a_G = dG/dξ·ξy, a_H = dH/dξ·ξz            -> shared partials
-//     eta pass  : a_F += dF/dη·ηx, ...                                     (in place)
-//     zeta pass : dFdx = a_F + dF/dζ·ζx, ...; rhs = 0 - ωJ((dFdx+dGdy+dHdz) - S)
-// which is exactly the left-to-right order of rhs.jl:1679-1696, so EXACT=true is bit-identical to
-// k_elem_node and to the oracle.  EXACT=false carries one partial (the sum over F,G,H) instead of
-// three: 1/3 less shared-memory traffic, sums associated differently (within the 1e-12 parity bar).
-// Records are streamed straight into registers (each double is used by exactly one thread); the
-// next group's records are pulled into L2 one iteration ahead with cp.async.bulk.prefetch.L2.
-// ------------------------------------------------------------------------------------------
-template <int NGL, class EQ, int EPB, bool EXACT>
-struct ElemPencilCfg {
-    static constexpr int N = NGL, NC = NGL * NGL, NP = NGL * NGL * NGL, NEQ = EQ::NEQ;
-    static constexpr int NT = round_up(EPB * NC, 32);
-    static constexpr int NPART = EXACT ? 3 : 1;
-    static constexpr int FLD_D = 3 * NEQ * NP;       // F,G,H of every equation at every node
-    static constexpr int PART_D = 2 * NPART * NP;    // partial sums, double buffered by equation parity
-    static constexpr size_t SMEM_BYTES = (size_t)EPB * (FLD_D + PART_D) * 8;
-};
-
+// L2 prefetch of a contiguous range (cp.async.bulk.prefetch: a uniform-datapath instruction, issued lane by lane)
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-template <int NGL, class EQ, int EPB, bool EXACT>
-static __global__ void __launch_bounds__(ElemPencilCfg<NGL, EQ, EPB, EXACT>::NT, 2)
-k_elem_pencil(const __grid_constant__ ElemArgs a) {
-    using C = ElemPencilCfg<NGL, EQ, EPB, EXACT>;
-    using G = Geo<3, NGL>;
-    constexpr int N = NGL, NC = C::NC, NP = C::NP, NEQ = C::NEQ, NPART = C::NPART, REC_BYTES = G::REC_BYTES;
-    static_assert(EQ::SRC_EQ >= -1, "pencil kernel keeps at most one source component in registers");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sm = reinterpret_cast<double *>(smem_raw);
-
-    const int t = threadIdx.x;
-    const bool active = t < EPB * NC;
-    const int slot = active ? t / NC : 0;
-    const int c = active ? t % NC : 0;
-    const int c0 = c % N, c1 = c / N;
-    double *X = sm + (size_t)slot * (C::FLD_D + C::PART_D);   // [3*NEQ][NP], node l = i + N*(j + N*k)
-    double *Pp = X + C::FLD_D;                                // [2][NPART][NP]
-    const int bx = N * c;              // xi-pencil:   node(m) = bx + m
-    const int by = c0 + NC * c1;       // eta-pencil:  node(m) = by + N*m
-    const int bz = c;                  // zeta-pencil: node(m) = bz + NC*m
-#define JX_D(m, i) a.dpsi[(m) + NGL * (i)]
-
-    const int64_t ngroups = (a.nelem + EPB - 1) / EPB;
-    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        {   // pull the next group's records towards L2 while this one computes
-            const int64_t pn = (g + gridDim.x) * EPB + t;
-            if (t < EPB && pn < a.nelem) {
-                const int64_t en = a.elist ? (int64_t)a.elist[pn] : pn;
-                prefetch_l2_bulk(a.rec + (size_t)en * REC_BYTES, REC_BYTES);
-            }
-        }
-        const int64_t pos = g * EPB + slot;
-        const bool live = active && pos < a.nelem;
-        const int64_t iel = live ? (a.elist ? (int64_t)a.elist[pos] : pos) : 0;
-        const double *rec = reinterpret_cast<const double *>(a.rec + (size_t)iel * REC_BYTES);
-        const int32_t *conn = reinterpret_cast<const int32_t *>(rec + G::NMET * NP);
-
-        double mx[3][N], my[3][N], mz[3][N], wj[N], mi[N], Ssrc[N];
-        int ip[N];
-        if (live) {
-#pragma unroll
-            for (int m = 0; m < N; ++m) ip[m] = __ldcs(conn + bz + NC * m);
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-#pragma unroll
-                for (int m = 0; m < N; ++m) {
-                    mx[q][m] = __ldcs(rec + (q * N + m) * NC + c);
-                    my[q][m] = __ldcs(rec + (3 * N + q * N + m) * NC + c);
-                    mz[q][m] = __ldcs(rec + (6 * N + q * N + m) * NC + c);
-                }
-#pragma unroll
-            for (int m = 0; m < N; ++m) wj[m] = __ldcs(rec + (9 * N + m) * NC + c);
-            // flux / source at the nodes of the zeta-pencil
-#pragma unroll
-            for (int m = 0; m < N; ++m) {
-                const int64_t node = ip[m];
-                double q[NEQ], qe[NEQ + 1], f[NEQ], gg[NEQ], h[NEQ];
-#pragma unroll
-                for (int e = 0; e < NEQ; ++e) q[e] = __ldg(a.u + (size_t)e * a.npoin + node);
-#pragma unroll
-                for (int e = 0; e <= NEQ; ++e) qe[e] = EQ::NEEDS_QE ? __ldg(a.qe + (size_t)e * a.npoin + node) : 0.0;
-                EQ::flux(a.phys, q, qe, f, gg, h);
-                const int l = bz + NC * m;
-#pragma unroll
-                for (int e = 0; e < NEQ; ++e) {
-                    X[(0 * NEQ + e) * NP + l] = f[e];
-                    X[(1 * NEQ + e) * NP + l] = gg[e];
-                    X[(2 * NEQ + e) * NP + l] = h[e];
-                }
-                Ssrc[m] = 0.0;
-                if constexpr (EQ::SRC_EQ >= 0) {
-                    if (a.lsource) {
-                        double xyz[3] = {0.0, 0.0, 0.0}, S[NEQ];
-                        if constexpr (EQ::NEEDS_XYZ) {
-#pragma unroll
-                            for (int d = 0; d < 3; ++d) xyz[d] = __ldg(a.coords + (size_t)d * a.npoin + node);
-                        }
-                        EQ::source(a.phys, q, qe, xyz, S);
-                        Ssrc[m] = S[EQ::SRC_EQ >= 0 ? EQ::SRC_EQ : 0];
-                    }
-                }
-                mi[m] = (a.atomics && a.Minv) ? __ldg(a.Minv + node) : 1.0;
-            }
-        }
-        __syncthreads();
-
-#pragma unroll 1
-        for (int e = 0; e < NEQ; ++e) {
-            double *Pe = Pp + (e & 1) * NPART * NP;
-            const double *Fe = X + (0 * NEQ + e) * NP, *Ge = X + (1 * NEQ + e) * NP, *He = X + (2 * NEQ + e) * NP;
-            if (live) {   // xi pass
-                double f[N], gg[N], h[N];
-#pragma unroll
-                for (int m = 0; m < N; ++m) { f[m] = Fe[bx + m]; gg[m] = Ge[bx + m]; h[m] = He[bx + m]; }
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    double dF = 0, dG = 0, dH = 0;
-#pragma unroll
-                    for (int m = 0; m < N; ++m) {
-                        dF = fma(JX_D(m, i), f[m], dF);
-                        dG = fma(JX_D(m, i), gg[m], dG);
-                        dH = fma(JX_D(m, i), h[m], dH);
-                    }
-                    if constexpr (EXACT) {
-                        Pe[0 * NP + bx + i] = dF * mx[0][i];
-                        Pe[1 * NP + bx + i] = dG * mx[1][i];
-                        Pe[2 * NP + bx + i] = dH * mx[2][i];
-                    } else {
-                        Pe[bx + i] = (dF * mx[0][i] + dG * mx[1][i]) + dH * mx[2][i];
-                    }
-                }
-            }
-            __syncthreads();
-            if (live) {   // eta pass
-                double f[N], gg[N], h[N];
-#pragma unroll
-                for (int m = 0; m < N; ++m) { f[m] = Fe[by + N * m]; gg[m] = Ge[by + N * m]; h[m] = He[by + N * m]; }
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    double dF = 0, dG = 0, dH = 0;
-#pragma unroll
-                    for (int m = 0; m < N; ++m) {
-                        dF = fma(JX_D(m, j), f[m], dF);
-                        dG = fma(JX_D(m, j), gg[m], dG);
-                        dH = fma(JX_D(m, j), h[m], dH);
-                    }
-                    const int o = by + N * j;
-                    if constexpr (EXACT) {
-                        Pe[0 * NP + o] = Pe[0 * NP + o] + dF * my[0][j];
-                        Pe[1 * NP + o] = Pe[1 * NP + o] + dG * my[1][j];
-                        Pe[2 * NP + o] = Pe[2 * NP + o] + dH * my[2][j];
-                    } else {
-                        Pe[o] = Pe[o] + ((dF * my[0][j] + dG * my[1][j]) + dH * my[2][j]);
-                    }
-                }
-            }
-            __syncthreads();
-            if (live) {   // zeta pass + output
-                double f[N], gg[N], h[N];
-#pragma unroll
-                for (int m = 0; m < N; ++m) { f[m] = Fe[bz + NC * m]; gg[m] = Ge[bz + NC * m]; h[m] = He[bz + NC * m]; }
-#pragma unroll
-                for (int k = 0; k < N; ++k) {
-                    double dF = 0, dG = 0, dH = 0;
-#pragma unroll
-                    for (int m = 0; m < N; ++m) {
-                        dF = fma(JX_D(m, k), f[m], dF);
-                        dG = fma(JX_D(m, k), gg[m], dG);
-                        dH = fma(JX_D(m, k), h[m], dH);
-                    }
-                    const int o = bz + NC * k;
-                    double r;
-                    if constexpr (EXACT) {
-                        const double dFdx = Pe[0 * NP + o] + dF * mz[0][k];
-                        const double dGdy = Pe[1 * NP + o] + dG * mz[1][k];
-                        const double dHdz = Pe[2 * NP + o] + dH * mz[2][k];
-                        r = (dFdx + dGdy) + dHdz;
-                    } else {
-                        r = Pe[o] + ((dF * mz[0][k] + dG * mz[1][k]) + dH * mz[2][k]);
-                    }
-                    const double S = (e == EQ::SRC_EQ) ? Ssrc[k] : 0.0;
-                    const double out = 0.0 - wj[k] * (r - S);
-                    if (!a.atomics) a.rhs_el[((size_t)iel * NEQ + e) * NP + o] = out;
-                    else atomicAdd(&a.du[(size_t)e * a.npoin + ip[k]], out * mi[k]);
-                }
-            }
-        }
-        __syncthreads();   // all pencils done with X before the next group's fluxes overwrite it
-    }
-#undef JX_D
-}
-
 // ------------------------------------------------------------------------------------------
-// Per-unique-node pre-pass of the pencil kernels: the part of user_flux! that depends on the node
+// Per-unique-node pre-pass of the team kernels: the part of user_flux! that depends on the node
 // only (the equation of state, one pow per node) is evaluated once per node instead of once per
 // element-node (x1.95 at nop=4), and -- in atomics mode -- the scatter target is zeroed in the same
 // sweep (replaces the memset).  Runs after the Dirichlet projection, like the flux evaluation it feeds.
@@ -751,329 +532,13 @@ static __global__ void k_node_aux(const __grid_constant__ AuxArgs a) {
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Fused per-element kernel, variant "wpencil" (3D, inviscid): the pencil kernel with ONE element per
-// CTA of round_up(n^2,32) threads (one warp at nop=4), many small CTAs per SM.  profiles/r01b showed the
-// 5-elements-per-128-threads pencil kernel latency bound at 2 warps per scheduler: 11 block barriers per
-// group couple all its warps, and the global-load phase of a group is exposed.  Here no barrier is wider
-// than one element, so 9-10 independent warps per SM overlap each other's load, flux and pencil phases.
-// The flux phase runs node-parallel over all 32 lanes; the pencil passes use n^2 of them.
-// ------------------------------------------------------------------------------------------
-#define JX_WPENCIL_MAXREG 224   // 9 one-warp CTAs per SM at nop=4
-#ifndef JX_WPENCIL_STAGE
-#define JX_WPENCIL_STAGE 0       // 1: gather q/aux of the next element with cp.async into shared staging (measured slower, profiles/r01e)
-#endif
-template <int NGL, class EQ, bool EXACT>
-struct ElemWPencilCfg {
-    static constexpr int N = NGL, NC = NGL * NGL, NP = NGL * NGL * NGL, NEQ = EQ::NEQ;
-    static constexpr int NT = round_up(NC, 32);
-    static constexpr int NPART = EXACT ? 3 : 1;
-    static constexpr int R = (NP + NT - 1) / NT;                 // flux rounds: node l = r*NT + t
-    static constexpr int NQ = EQ::NEQ - (EQ::FLUX_QMASK == ((1u << (EQ::NEQ - 1)) - 1u) ? 1 : 0);   // gathered q components
-    static constexpr int NCOMP = NQ + EQ::NAUX;                  // staged doubles per node
-    static constexpr int FLD_D = 3 * NEQ * NP;
-    static constexpr int PART_D = NPART * NP;
-    static constexpr int STG_D = JX_WPENCIL_STAGE ? R * NCOMP * NT : 0;
-    static constexpr size_t SMEM_BYTES = (size_t)(FLD_D + PART_D + NP + STG_D) * 8;
-};
-
+// cp.async (LDGSTS) helpers
 __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NPEND>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
-
-template <int NGL, class EQ, bool EXACT>
-static __global__ void __maxnreg__(JX_WPENCIL_MAXREG)
-k_elem_wpencil(const __grid_constant__ ElemArgs a) {
-    using C = ElemWPencilCfg<NGL, EQ, EXACT>;
-    using G = Geo<3, NGL>;
-    constexpr int N = NGL, NC = C::NC, NP = C::NP, NEQ = C::NEQ, REC_BYTES = G::REC_BYTES, NT = C::NT;
-    constexpr int R = C::R, NQ = C::NQ, NCOMP = C::NCOMP;
-    static_assert(EQ::SRC_EQ >= -1, "pencil kernels keep at most one source component");
-    static_assert(EQ::HAS_AUX, "the pencil kernels use the two-stage flux functors");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *X = reinterpret_cast<double *>(smem_raw);     // [3*NEQ][NP]
-    double *Pe = X + C::FLD_D;                            // [NPART][NP]
-    double *Sf = Pe + C::PART_D;                          // [NP] source of equation SRC_EQ
-    double *stg = Sf + NP;                                // [R][NCOMP][NT] gathers of the NEXT element (cp.async)
-
-    const int t = threadIdx.x;
-    const bool pl = t < NC;            // pencil lane
-    const int c = pl ? t : 0;
-    const int c0 = c % N, c1 = c / N;
-    const int bx = N * c, by = c0 + NC * c1, bz = c;
-    const bool fold = a.atomics && a.Minv != nullptr;
-#define JX_D(m, i) a.dpsi[(m) + NGL * (i)]
-// all N outputs of the three lines at once: 3N independent FMA chains, each accumulating in ascending m
-// exactly like the oracle's dot products
-#define JX_DERIV_ALL                                                        \
-    double dF[N], dG[N], dH[N];                                             \
-    _Pragma("unroll") for (int o_ = 0; o_ < N; ++o_) { dF[o_] = 0.0; dG[o_] = 0.0; dH[o_] = 0.0; } \
-    _Pragma("unroll") for (int m_ = 0; m_ < N; ++m_) {                      \
-        _Pragma("unroll") for (int o_ = 0; o_ < N; ++o_) {                  \
-            dF[o_] = fma(JX_D(m_, o_), f[m_], dF[o_]);                      \
-            dG[o_] = fma(JX_D(m_, o_), gg[m_], dG[o_]);                     \
-            dH[o_] = fma(JX_D(m_, o_), h[m_], dH[o_]);                      \
-        }                                                                   \
-    }
-    auto rec_of = [&](int64_t p) -> const double * {
-        return reinterpret_cast<const double *>(a.rec + (size_t)(a.elist ? (int64_t)a.elist[p] : p) * REC_BYTES);
-    };
-    // node ids of element p: flux-phase view (node l = r*NT + t) and zeta-pencil view (node c + NC*m)
-    auto load_ids = [&](int64_t p, int(&nd)[R], int(&ipz)[N]) {
-        const int32_t *cn = reinterpret_cast<const int32_t *>(rec_of(p) + G::NMET * NP);
-#pragma unroll
-        for (int r = 0; r < R; ++r) nd[r] = (r * NT + t < NP) ? __ldcs(cn + r * NT + t) : -1;
-#pragma unroll
-        for (int m = 0; m < N; ++m) ipz[m] = pl ? __ldcs(cn + bz + NC * m) : 0;
-    };
-    // q and the per-node EOS values of one element -> staging, asynchronously (no registers held)
-    auto issue_gathers = [&](const int(&nd)[R]) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (nd[r] >= 0) {
-                double *dst = stg + (size_t)r * NCOMP * NT + t;
-#pragma unroll
-                for (int e = 0; e < NQ; ++e) cp_async8(dst + e * NT, a.u + (size_t)e * a.npoin + nd[r]);
-#pragma unroll
-                for (int x = 0; x < EQ::NAUX; ++x) cp_async8(dst + (NQ + x) * NT, a.aux + (size_t)x * a.npoin + nd[r]);
-            }
-        }
-        cp_async_commit();
-    };
-
-    int ndn[R], ipn[N];
-    if ((int64_t)blockIdx.x < a.nelem) {
-        load_ids(blockIdx.x, ndn, ipn);
-        if (JX_WPENCIL_STAGE) issue_gathers(ndn);
-    }
-    for (int64_t pos = blockIdx.x; pos < a.nelem; pos += gridDim.x) {
-        const int64_t pn = pos + gridDim.x;
-        const int64_t iel = a.elist ? (int64_t)a.elist[pos] : pos;
-        const double *rec = rec_of(pos);
-        int nd[R], ip[N];
-#pragma unroll
-        for (int r = 0; r < R; ++r) nd[r] = ndn[r];
-#pragma unroll
-        for (int m = 0; m < N; ++m) ip[m] = ipn[m];
-
-        // metric terms of this thread's three pencils -> registers (in flight during the flux phase)
-        double mx[3][N], my[3][N], mz[3][N], wj[N], mi[N];
-        if (pl) {
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-#pragma unroll
-                for (int m = 0; m < N; ++m) {
-                    mx[q][m] = __ldcs(rec + (q * N + m) * NC + c);
-                    my[q][m] = __ldcs(rec + (3 * N + q * N + m) * NC + c);
-                    mz[q][m] = __ldcs(rec + (6 * N + q * N + m) * NC + c);
-                }
-#pragma unroll
-            for (int m = 0; m < N; ++m) wj[m] = __ldcs(rec + (9 * N + m) * NC + c);
-#pragma unroll
-            for (int m = 0; m < N; ++m) mi[m] = fold ? __ldg(a.Minv + ip[m]) : 1.0;
-        }
-        if (pn < a.nelem) {   // next element: node ids -> registers, record -> L2
-            load_ids(pn, ndn, ipn);
-            if (t == 0) prefetch_l2_bulk(rec_of(pn), REC_BYTES);
-        } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r) ndn[r] = -1;
-        }
-        // flux / source at every node, node-parallel; q and the per-node EOS values come either from the staged
-        // gathers (issued one element ago) or from direct gathers of all rounds issued together
-        double qa[R][NCOMP];
-        if (JX_WPENCIL_STAGE) {
-            cp_async_wait<0>();
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int x = 0; x < NCOMP; ++x) qa[r][x] = nd[r] >= 0 ? stg[((size_t)r * NCOMP + x) * NT + t] : 1.0;
-        } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int64_t node = nd[r] >= 0 ? nd[r] : 0;
-#pragma unroll
-                for (int e = 0; e < NQ; ++e) qa[r][e] = nd[r] >= 0 ? __ldg(a.u + (size_t)e * a.npoin + node) : 1.0;
-#pragma unroll
-                for (int x = 0; x < EQ::NAUX; ++x) qa[r][NQ + x] = nd[r] >= 0 ? __ldg(a.aux + (size_t)x * a.npoin + node) : 1.0;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int l = r * NT + t;
-            if (nd[r] >= 0) {
-                double q[NEQ], ax[EQ::NAUX], f[NEQ], gg[NEQ], h[NEQ];
-#pragma unroll
-                for (int e = 0; e < NEQ; ++e) q[e] = e < NQ ? qa[r][e < NQ ? e : 0] : 1.0;
-#pragma unroll
-                for (int x = 0; x < EQ::NAUX; ++x) ax[x] = qa[r][NQ + x];
-                EQ::flux_aux(a.phys, q, ax, f, gg, h);
-#pragma unroll
-                for (int e = 0; e < NEQ; ++e) {
-                    X[(0 * NEQ + e) * NP + l] = f[e];
-                    X[(1 * NEQ + e) * NP + l] = gg[e];
-                    X[(2 * NEQ + e) * NP + l] = h[e];
-                }
-                if constexpr (EQ::SRC_EQ >= 0) Sf[l] = a.lsource ? EQ::source_aux(a.phys, q, ax) : 0.0;
-            }
-        }
-        if (JX_WPENCIL_STAGE) issue_gathers(ndn);   // the staging slots were just consumed by their own threads
-        if (fold) {                    // atomics mode: M^-1 folded into the quadrature weight (one rounding)
-#pragma unroll
-            for (int m = 0; m < N; ++m) wj[m] = wj[m] * mi[m];
-        }
-        __syncthreads();
-
-#pragma unroll 1
-        for (int e = 0; e < NEQ; ++e) {
-            const double *Fe = X + (0 * NEQ + e) * NP, *Ge = X + (1 * NEQ + e) * NP, *He = X + (2 * NEQ + e) * NP;
-            if (pl) {   // xi pass
-                double f[N], gg[N], h[N];
-#pragma unroll
-                for (int m = 0; m < N; ++m) { f[m] = Fe[bx + m]; gg[m] = Ge[bx + m]; h[m] = He[bx + m]; }
-                JX_DERIV_ALL
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    if constexpr (EXACT) {
-                        Pe[0 * NP + bx + i] = dF[i] * mx[0][i];
-                        Pe[1 * NP + bx + i] = dG[i] * mx[1][i];
-                        Pe[2 * NP + bx + i] = dH[i] * mx[2][i];
-                    } else {
-                        Pe[bx + i] = (dF[i] * mx[0][i] + dG[i] * mx[1][i]) + dH[i] * mx[2][i];
-                    }
-                }
-            }
-            __syncthreads();
-            if (pl) {   // eta pass
-                double f[N], gg[N], h[N], pa[C::NPART][N];
-#pragma unroll
-                for (int m = 0; m < N; ++m) { f[m] = Fe[by + N * m]; gg[m] = Ge[by + N * m]; h[m] = He[by + N * m]; }
-#pragma unroll
-                for (int q = 0; q < C::NPART; ++q)
-#pragma unroll
-                    for (int j = 0; j < N; ++j) pa[q][j] = Pe[q * NP + by + N * j];
-                JX_DERIV_ALL
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    const int o = by + N * j;
-                    if constexpr (EXACT) {
-                        Pe[0 * NP + o] = pa[0][j] + dF[j] * my[0][j];
-                        Pe[1 * NP + o] = pa[1][j] + dG[j] * my[1][j];
-                        Pe[2 * NP + o] = pa[2][j] + dH[j] * my[2][j];
-                    } else {
-                        Pe[o] = pa[0][j] + ((dF[j] * my[0][j] + dG[j] * my[1][j]) + dH[j] * my[2][j]);
-                    }
-                }
-            }
-            __syncthreads();
-            if (pl) {   // zeta pass + output
-                double f[N], gg[N], h[N], pa[C::NPART][N], Sv[N];
-#pragma unroll
-                for (int m = 0; m < N; ++m) { f[m] = Fe[bz + NC * m]; gg[m] = Ge[bz + NC * m]; h[m] = He[bz + NC * m]; }
-#pragma unroll
-                for (int q = 0; q < C::NPART; ++q)
-#pragma unroll
-                    for (int k = 0; k < N; ++k) pa[q][k] = Pe[q * NP + bz + NC * k];
-#pragma unroll
-                for (int k = 0; k < N; ++k) Sv[k] = 0.0;
-                if constexpr (EQ::SRC_EQ >= 0) {
-                    if (e == EQ::SRC_EQ) {
-#pragma unroll
-                        for (int k = 0; k < N; ++k) Sv[k] = Sf[bz + NC * k];
-                    }
-                }
-                JX_DERIV_ALL
-                double *due = a.du + (size_t)e * a.npoin;
-                double *rhe = a.atomics ? nullptr : a.rhs_el + ((size_t)iel * NEQ + e) * NP + bz;
-#pragma unroll
-                for (int k = 0; k < N; ++k) {
-                    double r;
-                    if constexpr (EXACT) {
-                        const double dFdx = pa[0][k] + dF[k] * mz[0][k];
-                        const double dGdy = pa[1][k] + dG[k] * mz[1][k];
-                        const double dHdz = pa[2][k] + dH[k] * mz[2][k];
-                        r = (dFdx + dGdy) + dHdz;
-                    } else {
-                        r = pa[0][k] + ((dF[k] * mz[0][k] + dG[k] * mz[1][k]) + dH[k] * mz[2][k]);
-                    }
-                    const double out = 0.0 - wj[k] * (r - Sv[k]);
-                    if (rhe) rhe[NC * k] = out;
-                    else atomicAdd(due + ip[k], out);
-                }
-            }
-            __syncthreads();   // partials (and, after the last equation, the fields) are free again
-        }
-    }
-    cp_async_wait<0>();
-#undef JX_D
-#undef JX_DERIV_ALL
-}
-
-// ------------------------------------------------------------------------------------------
-// Fused per-element kernel, variant "gpencil" (3D, inviscid, exact order): pencils of a GROUP of EPB
-// elements flattened over the CTA's lanes.  profiles/r01e showed the one-element-per-warp kernel bound by
-// the LSU data pipe (86 % busy) with 25 of 32 lanes active at nop=4 and a 2-way bank conflict in its eta
-// pass.  Here
-//   * EPB*n^2 pencils fill the warps (nop=4: 5 elements = 125 pencils on 128 lanes, 97.6 %);
-//   * every pass decodes the lane id into (element slot, c0, c1) with its OWN digit order, chosen by
-//     scripts/analysis/bank_search2.py so that all three passes are bank-conflict free without padding
-//     (GPLayout);
-//   * the xi and eta passes write their metric-weighted derivatives into separate tiles (A1, A2) and the
-//     zeta pass adds (A1 + A2) + a3 -- the reference's left-to-right order (rhs.jl:1679-1696) with one block
-//     barrier less per equation and no read-modify-write of a partial;
-//   * the group record holds the metric terms as lane-major streams per pass (one coalesced LDG per stream),
-//     the node ids in the zeta-pass and flux-phase views, the quadrature weight omega*J and its pre-folded,
-//     negated product with M^-1 (atomics mode: no M^-1 gather, no "0 -" per output).
-// Arithmetic per output is the same IEEE sequence as k_elem_node / the oracle (deterministic mode:
-// bit-identical; atomics mode: identical up to the sign of zero and the order of the DSS sum).
-// ------------------------------------------------------------------------------------------
-struct DigitOrder { int d0, d1, d2; };     // digits fastest -> slowest; 0 = element slot s, 1 = c0, 2 = c1
-template <int NGL, int EPB>
-struct GPLayout {                           // generic: unpadded, element-major lanes in every pass
-    static constexpr int PJ = NGL, PK = NGL * NGL, ES = NGL * NGL * NGL;
-    static constexpr DigitOrder XI{1, 2, 0}, ETA{1, 2, 0}, ZETA{1, 2, 0};
-};
-template <>
-struct GPLayout<5, 5> {                     // conflict free in all three passes (bank_search2.py 5 5)
-    static constexpr int PJ = 5, PK = 25, ES = 125;
-    static constexpr DigitOrder XI{1, 2, 0}, ETA{2, 0, 1}, ZETA{0, 1, 2};
-};
-__host__ __device__ constexpr int gp_radix(int digit, int n, int epb) { return digit == 0 ? epb : n; }
-// multiplier of digit `which` in lane id p = s*M0 + c0*M1 + c1*M2
-__host__ __device__ constexpr int gp_mult(DigitOrder o, int which, int n, int epb) {
-    return o.d0 == which ? 1 : (o.d1 == which ? gp_radix(o.d0, n, epb) : gp_radix(o.d0, n, epb) * gp_radix(o.d1, n, epb));
-}
-__host__ __device__ constexpr int gp_digit(DigitOrder o, int which, int p, int n, int epb) {
-    return o.d0 == which ? p % gp_radix(o.d0, n, epb)
-                         : (o.d1 == which ? (p / gp_radix(o.d0, n, epb)) % gp_radix(o.d1, n, epb)
-                                          : p / (gp_radix(o.d0, n, epb) * gp_radix(o.d1, n, epb)));
-}
-
-template <int NGL, class EQ, int EPB>
-struct ElemGPencilCfg {
-    using L = GPLayout<NGL, EPB>;
-    static constexpr int N = NGL, NC = NGL * NGL, NP = NGL * NGL * NGL, NEQ = EQ::NEQ;
-    static constexpr int NPEN = EPB * NC;                       // pencils per group and direction
-    static constexpr int NT = round_up(NPEN, 32);
-    static constexpr int NNODE = EPB * NP;
-    static constexpr int R = (NNODE + NT - 1) / NT;             // flux rounds: group node n = r*NT + t
-    static constexpr int GB = round_up(EPB * L::ES, 2);         // doubles per field tile of a group
-    static constexpr bool PLAIN = (L::PJ == NGL && L::PK == NGL * NGL && L::ES == NGL * NGL * NGL);
-    static constexpr int NFLD = 3 * NEQ;
-    static constexpr int NTILE = NFLD + 6 + (EQ::SRC_EQ >= 0 ? 1 : 0);
-    static constexpr size_t SMEM_BYTES = (size_t)NTILE * GB * 8;
-    static constexpr int NQ = EQ::NEQ - (EQ::FLUX_QMASK == ((1u << (EQ::NEQ - 1)) - 1u) ? 1 : 0);
-    static constexpr int NCOMP = NQ + EQ::NAUX;
-    // group record: 11n lane-major double streams, then int32 zeta-view ids [n][NT], then flux-view ids [R*NT]
-    static constexpr int NSTREAM = 11 * NGL;
-    static constexpr int ZID_OFF = NSTREAM * NT * 8;
-    static constexpr int FID_OFF = ZID_OFF + NGL * NT * 4;
-    static constexpr int GROUP_BYTES = round_up(FID_OFF + R * NT * 4, 128);
-    static constexpr int MINB = (SMEM_BYTES + 1024) * 2 <= 233472 ? 2 : 1;
-};
 
 struct GroupRetileArgs {
     const double *src;        // one metric array [E, n, n, n], element fastest (device copy); slot >= 0
@@ -1082,14 +547,13 @@ struct GroupRetileArgs {
     const int64_t *connijk;   // slot -1
     char *rec;
     int64_t nelem;
-    int ngl, epb, nt, group_bytes, zid_off, fid_off;
-    int mult[3][3];           // [pass xi/eta/zeta][digit s/c0/c1]
+    int ngl, epb, group_bytes, zid_off, fid_off, z_off;
     int slot;                 // 0..8 metric term, 9 = Je (stored as omega*J), -1 = node ids, -2 = -(omega*J*Minv)
-    int layout;               // 4: k_elem_gpencil group records; 5: k_elem_team records (z_off = zeta streams)
-    int z_off;
 };
 
-// element-fastest Julia arrays -> group records; thread = (element, local node), element fastest
+// element-fastest Julia arrays -> element-group records of the team kernels (layout 5); thread = (element, local node),
+// element fastest.  Plane lane = k + n*(X + 3*s) holds xi_X, eta_X of plane k (streams n*j+i and n*n + n*j+i); zeta lane
+// c = i + n*j of slot s holds zeta_{x,y,z}, omega*J, -(omega*J*Minv) at node k; then the zeta-view and flux-view node ids.
 static __global__ void k_retile_group(GroupRetileArgs a) {
     const int n = a.ngl, np = n * n * n;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1103,242 +567,30 @@ static __global__ void k_retile_group(GroupRetileArgs a) {
     double *met = reinterpret_cast<double *>(rec);
     int32_t *zid = reinterpret_cast<int32_t *>(rec + a.zid_off);
     int32_t *fid = reinterpret_cast<int32_t *>(rec + a.fid_off);
-    const int pxi = s * a.mult[0][0] + j * a.mult[0][1] + k * a.mult[0][2];    // xi-pencil (j,k), node i
-    const int pet = s * a.mult[1][0] + i * a.mult[1][1] + k * a.mult[1][2];    // eta-pencil (i,k), node j
-    const int pze = s * a.mult[2][0] + i * a.mult[2][1] + j * a.mult[2][2];    // zeta-pencil (i,j), node k
     const size_t src = (size_t)iel + (size_t)a.nelem * l;
-    if (a.layout == 5) {
-        // team records (k_elem_team): plane lane = k + n*(X + 3*s) holds xi_X, eta_X of plane k (streams n*j+i and
-        // n*n + n*j+i); zeta lane c = i + n*j of round s holds zeta_{x,y,z}, omega*J, -(omega*J*Minv) at node k
-        const int nc = n * n, nstrz = 5 * n, c = i + n * j;
-        double *zs = reinterpret_cast<double *>(rec + a.z_off) + (size_t)s * nstrz * 32;
-        if (a.slot == -1) {
-            const int32_t ip = (int32_t)(a.connijk[src] - 1);
-            zid[(s * n + k) * 32 + c] = ip;
-            fid[s * np + l] = ip;
-        } else if (a.slot == -2) {
-            const int32_t ip = zid[(s * n + k) * 32 + c];
-            zs[(4 * n + k) * 32 + c] = -(zs[(3 * n + k) * 32 + c] * a.Minv[ip]);
-        } else if (a.slot < 6) {
-            const int X = a.slot % 3, lane = k + n * (X + 3 * s);
-            met[(size_t)((a.slot < 3 ? 0 : nc) + n * j + i) * 32 + lane] = a.src[src];
-        } else if (a.slot < 9) {
-            zs[((a.slot - 6) * n + k) * 32 + c] = a.src[src];
-        } else {
-            const double wjk = a.omega[j] * a.omega[k];      // rhs.jl:1636-1643
-            zs[(3 * n + k) * 32 + c] = a.omega[i] * wjk * a.src[src];
-        }
-        return;
-    }
+    const int nc = n * n, nstrz = 5 * n, c = i + n * j;
+    double *zs = reinterpret_cast<double *>(rec + a.z_off) + (size_t)s * nstrz * 32;
     if (a.slot == -1) {
         const int32_t ip = (int32_t)(a.connijk[src] - 1);
-        zid[k * a.nt + pze] = ip;
+        zid[(s * n + k) * 32 + c] = ip;
         fid[s * np + l] = ip;
     } else if (a.slot == -2) {
-        const int32_t ip = zid[k * a.nt + pze];
-        const double wJ = met[(size_t)(9 * n + k) * a.nt + pze];
-        met[(size_t)(10 * n + k) * a.nt + pze] = -(wJ * a.Minv[ip]);
-    } else if (a.slot < 3) {
-        met[(size_t)(a.slot * n + i) * a.nt + pxi] = a.src[src];
+        const int32_t ip = zid[(s * n + k) * 32 + c];
+        zs[(4 * n + k) * 32 + c] = -(zs[(3 * n + k) * 32 + c] * a.Minv[ip]);
     } else if (a.slot < 6) {
-        met[(size_t)(3 * n + (a.slot - 3) * n + j) * a.nt + pet] = a.src[src];
+        const int X = a.slot % 3, lane = k + n * (X + 3 * s);
+        met[(size_t)((a.slot < 3 ? 0 : nc) + n * j + i) * 32 + lane] = a.src[src];
     } else if (a.slot < 9) {
-        met[(size_t)(6 * n + (a.slot - 6) * n + k) * a.nt + pze] = a.src[src];
+        zs[((a.slot - 6) * n + k) * 32 + c] = a.src[src];
     } else {
         const double wjk = a.omega[j] * a.omega[k];      // rhs.jl:1636-1643
-        met[(size_t)(9 * n + k) * a.nt + pze] = a.omega[i] * wjk * a.src[src];
+        zs[(3 * n + k) * 32 + c] = a.omega[i] * wjk * a.src[src];
     }
-}
-
-template <int NGL, class EQ, int EPB>
-static __global__ void __launch_bounds__(ElemGPencilCfg<NGL, EQ, EPB>::NT, ElemGPencilCfg<NGL, EQ, EPB>::MINB)
-k_elem_gpencil(const __grid_constant__ ElemArgs a) {
-    using C = ElemGPencilCfg<NGL, EQ, EPB>;
-    using L = typename C::L;
-    constexpr int N = NGL, NC = C::NC, NP = C::NP, NEQ = C::NEQ, NT = C::NT, R = C::R, GB = C::GB;
-    constexpr int NQ = C::NQ, NCOMP = C::NCOMP;
-    constexpr int PJ = L::PJ, PK = L::PK, ES = L::ES;
-    static_assert(EQ::SRC_EQ >= -1, "pencil kernels keep at most one source component");
-    static_assert(EQ::HAS_AUX, "the pencil kernels use the two-stage flux functors");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *X = reinterpret_cast<double *>(smem_raw);     // [3*NEQ][GB] fluxes F, G, H of every equation
-    double *A = X + (size_t)C::NFLD * GB;                 // [6][GB]: A1 (xi) F,G,H then A2 (eta) F,G,H
-    double *Sf = A + 6 * GB;                              // [GB] source of equation SRC_EQ
-
-    const int t = threadIdx.x;
-    const bool pen = t < C::NPEN;
-    const int p = pen ? t : 0;
-    // per-pass lane decode: (element slot, c0, c1)
-    const int sx = gp_digit(L::XI, 0, p, N, EPB), jx_ = gp_digit(L::XI, 1, p, N, EPB), kx = gp_digit(L::XI, 2, p, N, EPB);
-    const int sy = gp_digit(L::ETA, 0, p, N, EPB), iy = gp_digit(L::ETA, 1, p, N, EPB), ky = gp_digit(L::ETA, 2, p, N, EPB);
-    const int sz = gp_digit(L::ZETA, 0, p, N, EPB), iz = gp_digit(L::ZETA, 1, p, N, EPB), jz = gp_digit(L::ZETA, 2, p, N, EPB);
-    const int bx = sx * ES + PJ * jx_ + PK * kx;       // xi-pencil:   node(m) = bx + m
-    const int by = sy * ES + iy + PK * ky;             // eta-pencil:  node(m) = by + PJ*m
-    const int bz = sz * ES + iz + PJ * jz;             // zeta-pencil: node(m) = bz + PK*m
-    const bool fold = a.atomics && a.Minv != nullptr;
-#define JX_D(m, i) a.dpsi[(m) + NGL * (i)]
-#define JX_DERIV_ALL                                                        \
-    double dF[N], dG[N], dH[N];                                             \
-    _Pragma("unroll") for (int o_ = 0; o_ < N; ++o_) { dF[o_] = 0.0; dG[o_] = 0.0; dH[o_] = 0.0; } \
-    _Pragma("unroll") for (int m_ = 0; m_ < N; ++m_) {                      \
-        _Pragma("unroll") for (int o_ = 0; o_ < N; ++o_) {                  \
-            dF[o_] = fma(JX_D(m_, o_), f[m_], dF[o_]);                      \
-            dG[o_] = fma(JX_D(m_, o_), gg[m_], dG[o_]);                     \
-            dH[o_] = fma(JX_D(m_, o_), h[m_], dH[o_]);                      \
-        }                                                                   \
-    }
-    const int64_t ngroups = (a.nelem + EPB - 1) / EPB;
-    auto fid_of = [&](int64_t g) { return reinterpret_cast<const int32_t *>(a.rec + (size_t)g * C::GROUP_BYTES + C::FID_OFF); };
-    int fidn[R];
-    if ((int64_t)blockIdx.x < ngroups) {
-        const int32_t *fi = fid_of(blockIdx.x);
-#pragma unroll
-        for (int r = 0; r < R; ++r) fidn[r] = __ldcs(fi + r * NT + t);
-    }
-    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        const int64_t gn = g + gridDim.x;
-        const int64_t e0 = g * EPB;
-        const int cnt = (int)(a.nelem - e0 < EPB ? a.nelem - e0 : EPB);
-        const char *rec = a.rec + (size_t)g * C::GROUP_BYTES;
-        const double *met = reinterpret_cast<const double *>(rec);
-        const int32_t *zid = reinterpret_cast<const int32_t *>(rec + C::ZID_OFF);
-
-        // gathers of q and the per-node EOS values, all rounds in flight together
-        double qa[R][NCOMP];
-        bool nv[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            nv[r] = r * NT + t < cnt * NP;
-            const int64_t node = nv[r] ? fidn[r] : 0;
-#pragma unroll
-            for (int e = 0; e < NQ; ++e) qa[r][e] = nv[r] ? __ldg(a.u + (size_t)e * a.npoin + node) : 1.0;
-#pragma unroll
-            for (int x = 0; x < EQ::NAUX; ++x) qa[r][NQ + x] = nv[r] ? __ldg(a.aux + (size_t)x * a.npoin + node) : 1.0;
-        }
-        // metric terms of this lane's three pencils, quadrature weights and zeta-view node ids -> registers
-        // (the streams are lane-major and padded to NT columns: no predicate needed)
-        double mx[3][N], my[3][N], mz[3][N], wj[N];
-        int ip[N];
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-#pragma unroll
-            for (int m = 0; m < N; ++m) {
-                mx[q][m] = __ldcs(met + (q * N + m) * NT + t);
-                my[q][m] = __ldcs(met + (3 * N + q * N + m) * NT + t);
-                mz[q][m] = __ldcs(met + (6 * N + q * N + m) * NT + t);
-            }
-#pragma unroll
-        for (int m = 0; m < N; ++m) {
-            wj[m] = __ldcs(met + ((fold ? 10 : 9) * N + m) * NT + t);
-            ip[m] = __ldcs(zid + m * NT + t);
-        }
-        if (gn < ngroups) {   // next group: flux-view node ids -> registers, record -> L2
-            const int32_t *fi = fid_of(gn);
-#pragma unroll
-            for (int r = 0; r < R; ++r) fidn[r] = __ldcs(fi + r * NT + t);
-            constexpr int CH = 2048;
-            for (int off = t * CH; off < C::FID_OFF; off += NT * CH)
-                prefetch_l2_bulk(a.rec + (size_t)gn * C::GROUP_BYTES + off, (C::FID_OFF - off) < CH ? (C::FID_OFF - off) : CH);
-        }
-        // flux / source at every node of the group, node-parallel
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (nv[r]) {
-                const int n = r * NT + t;          // group node n = slot*NP + l
-                int ad = n;
-                if constexpr (!C::PLAIN) {
-                    const int sl = n / NP, l = n % NP;
-                    ad = sl * ES + (l % N) + PJ * ((l / N) % N) + PK * (l / NC);
-                }
-                double q[NEQ], ax[EQ::NAUX], f[NEQ], gg[NEQ], h[NEQ];
-#pragma unroll
-                for (int e = 0; e < NEQ; ++e) q[e] = e < NQ ? qa[r][e < NQ ? e : 0] : 1.0;
-#pragma unroll
-                for (int x = 0; x < EQ::NAUX; ++x) ax[x] = qa[r][NQ + x];
-                EQ::flux_aux(a.phys, q, ax, f, gg, h);
-#pragma unroll
-                for (int e = 0; e < NEQ; ++e) {
-                    X[(0 * NEQ + e) * GB + ad] = f[e];
-                    X[(1 * NEQ + e) * GB + ad] = gg[e];
-                    X[(2 * NEQ + e) * GB + ad] = h[e];
-                }
-                if constexpr (EQ::SRC_EQ >= 0) Sf[ad] = a.lsource ? EQ::source_aux(a.phys, q, ax) : 0.0;
-            }
-        }
-        __syncthreads();
-
-        const bool lx = pen && sx < cnt, ly = pen && sy < cnt, lz = pen && sz < cnt;
-#pragma unroll 1
-        for (int e = 0; e < NEQ; ++e) {
-            const double *Fe = X + (0 * NEQ + e) * GB, *Ge = X + (1 * NEQ + e) * GB, *He = X + (2 * NEQ + e) * GB;
-            if (lx) {   // xi pass: A1 = dF/dxi * xi_x, dG/dxi * xi_y, dH/dxi * xi_z
-                double f[N], gg[N], h[N];
-#pragma unroll
-                for (int m = 0; m < N; ++m) { f[m] = Fe[bx + m]; gg[m] = Ge[bx + m]; h[m] = He[bx + m]; }
-                JX_DERIV_ALL
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    A[0 * GB + bx + i] = dF[i] * mx[0][i];
-                    A[1 * GB + bx + i] = dG[i] * mx[1][i];
-                    A[2 * GB + bx + i] = dH[i] * mx[2][i];
-                }
-            }
-            if (ly) {   // eta pass: A2
-                double f[N], gg[N], h[N];
-#pragma unroll
-                for (int m = 0; m < N; ++m) { f[m] = Fe[by + PJ * m]; gg[m] = Ge[by + PJ * m]; h[m] = He[by + PJ * m]; }
-                JX_DERIV_ALL
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    A[3 * GB + by + PJ * j] = dF[j] * my[0][j];
-                    A[4 * GB + by + PJ * j] = dG[j] * my[1][j];
-                    A[5 * GB + by + PJ * j] = dH[j] * my[2][j];
-                }
-            }
-            __syncthreads();
-            if (lz) {   // zeta pass + output
-                double f[N], gg[N], h[N], a1[3][N], a2[3][N], Sv[N];
-#pragma unroll
-                for (int m = 0; m < N; ++m) { f[m] = Fe[bz + PK * m]; gg[m] = Ge[bz + PK * m]; h[m] = He[bz + PK * m]; }
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-#pragma unroll
-                    for (int k = 0; k < N; ++k) { a1[q][k] = A[q * GB + bz + PK * k]; a2[q][k] = A[(3 + q) * GB + bz + PK * k]; }
-#pragma unroll
-                for (int k = 0; k < N; ++k) Sv[k] = 0.0;
-                if constexpr (EQ::SRC_EQ >= 0) {
-                    if (e == EQ::SRC_EQ) {
-#pragma unroll
-                        for (int k = 0; k < N; ++k) Sv[k] = Sf[bz + PK * k];
-                    }
-                }
-                JX_DERIV_ALL
-                double *due = a.du + (size_t)e * a.npoin;
-                double *rhe = a.atomics ? nullptr : a.rhs_el + ((size_t)(e0 + sz) * NEQ + e) * NP + iz + N * jz;
-#pragma unroll
-                for (int k = 0; k < N; ++k) {
-                    const double dFdx = (a1[0][k] + a2[0][k]) + dF[k] * mz[0][k];
-                    const double dGdy = (a1[1][k] + a2[1][k]) + dG[k] * mz[1][k];
-                    const double dHdz = (a1[2][k] + a2[2][k]) + dH[k] * mz[2][k];
-                    const double r = (dFdx + dGdy) + dHdz;
-                    if (fold) atomicAdd(due + ip[k], wj[k] * (r - Sv[k]));          // wj = -(omega*J*Minv)
-                    else {
-                        const double out = 0.0 - wj[k] * (r - Sv[k]);
-                        if (rhe) rhe[NC * k] = out;
-                        else atomicAdd(due + ip[k], out);
-                    }
-                }
-            }
-            __syncthreads();   // A tiles (and, after the last equation, the flux tiles) are free again
-        }
-    }
-#undef JX_D
-#undef JX_DERIV_ALL
 }
 
 // ------------------------------------------------------------------------------------------
 // Fused per-element kernel, variant "team" (3D, inviscid, exact order): specialised warps of one CTA work on a
-// group of EPB elements (2 at nop=4).  profiles/r01f: the pencil kernels are bound by the LSU data pipe --
+// group of EPB elements (2 at nop=4).  profiles/r01f: the round-1 pencil kernels (one thread per LGL line; removed in round 2) were bound by the LSU data pipe --
 // 24 doubles cross shared memory per node and equation (9 line loads, 12 partial-product exchanges, 3 flux
 // stores).  Here
 //   * the PLANE warp: lane (slot, X in {F,G,H}, k) keeps the 25 values of plane k of field X_e in registers and
@@ -1406,8 +658,8 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
     constexpr int SPW = C::SPW;
     constexpr int N = NGL, NC = C::NC, NP = C::NP, NEQ = C::NEQ, NT = C::NT, R = C::R, GB = C::GB, EPB = C::EPB;
     constexpr int NQ = C::NQ, NCOMP = C::NCOMP, NSTRZ = C::NSTRZ;
-    static_assert(EQ::SRC_EQ >= -1, "pencil kernels keep at most one source component");
-    static_assert(EQ::HAS_AUX, "the pencil kernels use the two-stage flux functors");
+    static_assert(EQ::SRC_EQ >= -1, "team kernels keep at most one source component");
+    static_assert(EQ::HAS_AUX, "the team kernels use the two-stage flux functors");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *X = reinterpret_cast<double *>(smem_raw);     // [NEQ][3][GB]: F_e, G_e, H_e adjacent
     double *B = X + (size_t)C::NFLD * GB;                 // [2][3][GB]
@@ -1934,3 +1186,5 @@ static __global__ void k_add_sel(double *a, int64_t npoin, int m, const int64_t 
 }  // namespace jx
 
 #include "jx_team2.cuh"
+#include "jx_tri.cuh"
+#include "jx_visc.cuh"

@@ -65,126 +65,6 @@ KernelSet make_node_set(int eq_id, int lpert, int jxpow) {
     return ks;
 }
 
-// variant 1 (EXACT) / 2 (single partial): pencil kernel, 3D inviscid
-template <int NGL, class EQ, bool EXACT>
-struct PencilKernel {
-    static constexpr int NC = NGL * NGL;
-    static constexpr int EPB = NC >= 128 ? 1 : (128 / NC);
-    using C = ElemPencilCfg<NGL, EQ, EPB, EXACT>;
-    static cudaError_t prepare() {
-        return cudaFuncSetAttribute(k_elem_pencil<NGL, EQ, EPB, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)C::SMEM_BYTES);
-    }
-    static int max_blocks() {
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_pencil<NGL, EQ, EPB, EXACT>, C::NT, C::SMEM_BYTES);
-        return nb;
-    }
-    static void launch(const ElemArgs &a, int grid, cudaStream_t s) {
-        k_elem_pencil<NGL, EQ, EPB, EXACT><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
-    }
-};
-
-template <int NGL, class EQ, bool EXACT>
-KernelSet make_pencil_set(int eq_id, int lpert, int jxpow) {
-    using K = PencilKernel<NGL, EQ, EXACT>;
-    KernelSet ks;
-    ks.nsd = 3; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = 0; ks.variant = EXACT ? 1 : 2;
-    ks.neq = EQ::NEQ;
-    ks.elems_per_block = K::EPB;
-    ks.rec_layout = 1;
-    ks.nthreads = K::C::NT;
-    ks.smem_bytes = K::C::SMEM_BYTES;
-    ks.prepare = &K::prepare;
-    ks.max_blocks_per_sm = &K::max_blocks;
-    ks.launch_elem = &K::launch;
-    ks.launch_bc = &launch_bc_t<EQ>;
-    ks.launch_gather = &launch_gather_t<EQ::NEQ>;
-    ks.launch_aux = nullptr;
-    return ks;
-}
-
-// variant 3 (EXACT) / 4 (single partial): one element per CTA pencil kernel, 3D inviscid
-template <int NGL, class EQ, bool EXACT>
-struct WPencilKernel {
-    using C = ElemWPencilCfg<NGL, EQ, EXACT>;
-    static cudaError_t prepare() {
-        return cudaFuncSetAttribute(k_elem_wpencil<NGL, EQ, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)C::SMEM_BYTES);
-    }
-    static int max_blocks() {
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_wpencil<NGL, EQ, EXACT>, C::NT, C::SMEM_BYTES);
-        return nb;
-    }
-    static void launch(const ElemArgs &a, int grid, cudaStream_t s) {
-        k_elem_wpencil<NGL, EQ, EXACT><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
-    }
-};
-
-template <int NGL, class EQ, bool EXACT>
-KernelSet make_wpencil_set(int eq_id, int lpert, int jxpow) {
-    using K = WPencilKernel<NGL, EQ, EXACT>;
-    KernelSet ks;
-    ks.nsd = 3; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = 0; ks.variant = EXACT ? 3 : 4;
-    ks.neq = EQ::NEQ;
-    ks.elems_per_block = 1;
-    ks.rec_layout = 1;
-    ks.nthreads = K::C::NT;
-    ks.smem_bytes = K::C::SMEM_BYTES;
-    ks.prepare = &K::prepare;
-    ks.max_blocks_per_sm = &K::max_blocks;
-    ks.launch_elem = &K::launch;
-    ks.launch_bc = &launch_bc_t<EQ>;
-    ks.launch_gather = &launch_gather_t<EQ::NEQ>;
-    ks.launch_aux = EQ::HAS_AUX ? &launch_aux_t<EQ> : nullptr;
-    return ks;
-}
-
-// variant 5 (group of elements per CTA, lanes full) / 6 (one element per CTA): group-pencil kernel, 3D inviscid,
-// exact order
-template <int NGL, class EQ, int EPB>
-struct GPencilKernel {
-    using C = ElemGPencilCfg<NGL, EQ, EPB>;
-    static cudaError_t prepare() {
-        return cudaFuncSetAttribute(k_elem_gpencil<NGL, EQ, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)C::SMEM_BYTES);
-    }
-    static int max_blocks() {
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_gpencil<NGL, EQ, EPB>, C::NT, C::SMEM_BYTES);
-        return nb;
-    }
-    static void launch(const ElemArgs &a, int grid, cudaStream_t s) {
-        k_elem_gpencil<NGL, EQ, EPB><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
-    }
-};
-
-template <int NGL, class EQ, int EPB>
-KernelSet make_gpencil_set(int eq_id, int lpert, int jxpow, int variant) {
-    using K = GPencilKernel<NGL, EQ, EPB>;
-    using C = typename K::C;
-    using L = typename C::L;
-    KernelSet ks;
-    ks.nsd = 3; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = 0; ks.variant = variant;
-    ks.neq = EQ::NEQ;
-    ks.elems_per_block = EPB;
-    ks.rec_layout = 4;
-    ks.nthreads = C::NT;
-    ks.smem_bytes = C::SMEM_BYTES;
-    ks.prepare = &K::prepare;
-    ks.max_blocks_per_sm = &K::max_blocks;
-    ks.launch_elem = &K::launch;
-    ks.launch_bc = &launch_bc_t<EQ>;
-    ks.launch_gather = &launch_gather_t<EQ::NEQ>;
-    ks.launch_aux = &launch_aux_t<EQ>;
-    ks.group_bytes = C::GROUP_BYTES; ks.group_nt = C::NT; ks.zid_off = C::ZID_OFF; ks.fid_off = C::FID_OFF;
-    const DigitOrder ord[3] = {L::XI, L::ETA, L::ZETA};
-    for (int ps = 0; ps < 3; ++ps)
-        for (int d = 0; d < 3; ++d) ks.group_mult[ps][d] = gp_mult(ord[ps], d, NGL, EPB);
-    return ks;
-}
-
 // variant 8 (one plane warp, one zeta warp per element slot) / 9 (two plane warps): plane-role + zeta-pencil-role warp team per element
 // group, 3D inviscid, exact order; the scatter mode (rhs_el store / RED.ADD / RED.ADD with folded M^-1) is a
 // template parameter chosen per launch
@@ -274,7 +154,7 @@ KernelSet make_team2_set(int eq_id, int lpert, int jxpow, int variant) {
     ks.nsd = 3; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = 0; ks.variant = variant;
     ks.neq = EQ::NEQ;
     ks.elems_per_block = C::EPB;
-    ks.rec_layout = 5;
+    ks.rec_layout = 6;                 // layout 5 + row-run tables (build_row_runs)
     ks.nthreads = C::NT;
     ks.smem_bytes = C::SMEM_BYTES;
     ks.prepare = &K::prepare;
@@ -289,6 +169,83 @@ KernelSet make_team2_set(int eq_id, int lpert, int jxpow, int variant) {
     ks.wpos_off = L::WPOS_OFF; ks.runi_off = L::RUNI_OFF; ks.runr_off = L::RUNR_OFF; ks.runl_off = L::RUNL_OFF; ks.nrun_off = L::NRUN_OFF;
     ks.maxrun = L::MAXRUN;
     ks.has_dyn = 1;
+    return ks;
+}
+
+// variant 12: k_elem_tri (nop = 7): xi-, eta- and zeta-pencil roles of 64 lanes each, one element per CTA
+template <int NGL, class EQ>
+struct TriKernel {
+    using C = ElemTriCfg<NGL, EQ>;
+    static cudaError_t prepare() {
+        cudaError_t e = cudaFuncSetAttribute(k_elem_tri<NGL, EQ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_tri<NGL, EQ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_tri<NGL, EQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        return e;
+    }
+    static int max_blocks() {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_tri<NGL, EQ, 2>, C::NT, C::SMEM_BYTES);
+        return nb;
+    }
+    static void launch(const ElemArgs &a, int grid, cudaStream_t s) {
+        if (!a.atomics) k_elem_tri<NGL, EQ, 0><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+        else if (a.Minv == nullptr) k_elem_tri<NGL, EQ, 1><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+        else k_elem_tri<NGL, EQ, 2><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
+    }
+};
+
+template <int NGL, class EQ>
+KernelSet make_tri_set(int eq_id, int lpert, int jxpow, int variant) {
+    using K = TriKernel<NGL, EQ>;
+    using C = typename K::C;
+    KernelSet ks;
+    ks.nsd = 3; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = 0; ks.variant = variant;
+    ks.neq = EQ::NEQ;
+    ks.elems_per_block = 1;
+    ks.rec_layout = 7;
+    ks.nthreads = C::NT;
+    ks.smem_bytes = C::SMEM_BYTES;
+    ks.prepare = &K::prepare;
+    ks.max_blocks_per_sm = &K::max_blocks;
+    ks.launch_elem = &K::launch;
+    ks.launch_bc = &launch_bc_t<EQ>;
+    ks.launch_gather = &launch_gather_t<EQ::NEQ>;
+    ks.launch_aux = &launch_aux_t<EQ>;
+    ks.group_bytes = C::REC_BYTES; ks.zid_off = C::ZID_OFF; ks.fid_off = C::FID_OFF;
+    return ks;
+}
+
+// AV viscous pass of its own (k_visc_team) attached to an inviscid team set: variant 9 with lvisc = 1
+template <int NGL, class EQ>
+struct ViscKernel {
+    using C = ViscTeamCfg<NGL, EQ>;
+    static cudaError_t prepare() {
+        cudaError_t e = cudaFuncSetAttribute(k_visc_team<NGL, EQ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_visc_team<NGL, EQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        return e;
+    }
+    static int max_blocks() {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_visc_team<NGL, EQ, 2>, C::NT, C::SMEM_BYTES);
+        return nb;
+    }
+    static void launch(const ElemArgs &a, const ViscArgs &v, int grid, cudaStream_t s) {
+        if (!a.atomics) k_visc_team<NGL, EQ, 0><<<grid, C::NT, C::SMEM_BYTES, s>>>(a, v);
+        else k_visc_team<NGL, EQ, 2><<<grid, C::NT, C::SMEM_BYTES, s>>>(a, v);
+    }
+};
+
+template <int NGL, class EQ, int ZW, int PW>
+KernelSet make_team_visc_set(int eq_id, int lpert, int jxpow, int variant) {
+    KernelSet ks = make_team_set<NGL, EQ, ZW, PW>(eq_id, lpert, jxpow, variant);
+    using V = ViscKernel<NGL, EQ>;
+    ks.lvisc = 1;
+    ks.has_dyn = 0;                       // the viscous pass walks all pairs: no interface-first split
+    ks.launch_visc = &V::launch;
+    ks.visc_max_blocks = &V::max_blocks;
+    ks.visc_prepare = &V::prepare;
+    ks.visc_group_bytes = V::C::GROUP_BYTES; ks.visc_zslot_bytes = V::C::ZSLOT_BYTES; ks.visc_zid_off = V::C::ZID_OFF;
+    ks.visc_fid_off = V::C::FID_OFF;
     return ks;
 }
 

@@ -71,7 +71,7 @@ def params_setup(sem, qe, inputs, *, device=0, rank=0, nranks=1, nccl_uid=None, 
         mu[:] = np.broadcast_to(np.asarray(inputs.get("mu", 0.0), float), (neqs,))
     if phys is None:
         phys = PhysicalConst().packed()
-    ctx = capi.Context(device=device, rank=rank, nranks=nranks, nccl_uid=nccl_uid)
+    ctx = capi.Context(device=device, rank=rank, nranks=nranks, nccl_uid=nccl_uid, nccl_max_ctas=overlap if nranks > 1 else 0)
     try:
         ctx.set_option(capi.JX_OPT_DSS_MODE, dss_mode)
         ctx.set_option(capi.JX_OPT_POW_MODE, pow_mode)

@@ -1,18 +1,26 @@
 # rhs_b200.jl -- reference-side binding of libjexrhs (include/jexrhs.h) for Jexpresso.
 #
-# Drop this file into src/kernel/operators/ and `include` it after rhs.jl.  It adds ONE backend
-# branch to the reference: when `inputs[:backend]` is `B200()` the ODEProblem is built on
-# `rhs_b200!` instead of `rhs!` (src/kernel/solvers/TimeIntegrators.jl:210-213), everything else
-# (mesh, setup, integrator, callbacks, I/O) is untouched.  Cannot be executed in the authoring
-# image (no Julia); its ctypes twin jexpresso_b200/{capi,rhs}.py is what the tests run.
+# `include` this file inside `module Jexpresso` after src/kernel/operators/rhs.jl.  It adds ONE backend branch to the
+# reference: when `inputs[:backend]` is `B200()` the ODEProblem is built on `rhs_b200!` with `B200Params(params, ctx)` as its
+# parameter object instead of `rhs!` with `params` (src/kernel/solvers/TimeIntegrators.jl:210-213); everything else (mesh,
+# setup, integrator, callbacks, I/O) is untouched.  It cannot be executed in the authoring image (no Julia); its ctypes twin
+# jexpresso_b200/{capi,rhs}.py is what the tests run, and tests/test_julia_shim_cpu.py checks that every `params.*` field
+# and `inputs[:*]` key read below exists in the reference (params_setup.jl:442-479, mod_inputs.jl, run.jl:160-170).
 module JexRHSB200
 
 const LIB = get(ENV, "JEXRHS_LIB", "libjexrhs.so")
 const Ctx = Ptr{Cvoid}
+const J = parentmodule(@__MODULE__)                # Jexpresso: PHYS_CONST (rhs.jl:11), PERT (SOL_VARS_TYPE tags)
 
 struct B200 end                                    # value for inputs[:backend]
 
-const EQ_IDS = Dict("CompEuler" => 0, "CompEulerEnergy" => 1, "AdvDiff" => 2, "ShallowWater" => 3)
+"What the ODEProblem carries instead of `params`: the reference's NamedTuple plus the device context and a host buffer."
+struct B200Params{P}
+    params::P
+    ctx::Ctx
+    dubuf::Vector{Float64}                         # staging for `du` objects without a pointer (ArrayFuse, see rhs_b200!)
+end
+
 const SCHEMES = Dict("CarpenterKennedy2N54" => 0, "SSPRK54" => 1, "SSPRK33" => 2)
 const PERIODIC = ("periodicx", "periodicy", "periodicz", "periodic1", "periodic2", "periodic3", "Laguerre")
 
@@ -23,32 +31,73 @@ function check(ctx::Ctx, rc::Cint)
     error("libjexrhs error $rc: " * unsafe_string(pointer(buf)))
 end
 
+"""
+Equation-set id of include/jexrhs.h.  The reference names the equation directory in `inputs[:_parsed_equations]`
+(run.jl:167); the total-energy form is CompEuler with `inputs[:energy_equation] == "energy"` (mod_inputs.jl:1027-1028,
+run.jl:305-314).
+"""
+function equation_id(inputs)
+    eqs = inputs[:_parsed_equations]
+    eqs == "CompEuler"    && return inputs[:energy_equation] == "theta" ? 0 : 1
+    eqs == "AdvDiff"      && return 2
+    eqs == "ShallowWater" && return 3
+    error("libjexrhs has no device functor registered for problems/$eqs")
+end
+
+"""
+The 16 packed constants of jx_set_problem: [C0, γ, g, Rair, cp, cv, pref, γ-1] from PhysicalConst{Float64}() (rhs.jl:11,
+globalConstantsPhysics.jl:3-62), then the constants the case hooks hard-code (they are literals inside user_flux.jl /
+user_source.jl, not inputs): slots 8-10 the AdvDiff wind; slots 9-15 the ShallowWater cone and wet/dry constants
+(jexpresso_b200/physics.py: advdiff_packed, swe_packed).  `inputs[:b200_case_constants]` (a Vector{Float64} for slots
+8-15) overrides the table below for cases it does not list.
+"""
+function packed_constants(inputs)
+    PC = J.PHYS_CONST
+    phys = zeros(Float64, 16)
+    phys[1:8] .= (PC.C0, PC.γ, PC.g, PC.Rair, PC.cp, PC.cv, PC.pref, PC.γm1)
+    if haskey(inputs, :b200_case_constants)
+        phys[9:16] .= inputs[:b200_case_constants]
+    else
+        eqs, case = inputs[:_parsed_equations], inputs[:_parsed_case_name]
+        if eqs == "AdvDiff"
+            wind = case == "kopriva" ? (0.5, 1.0, 0.0) :                       # problems/AdvDiff/kopriva/user_flux.jl:1-16
+                   case == "3d_periodic" ? (0.2, 0.2, 0.0) :                    # problems/AdvDiff/3d_periodic/user_flux.jl:1-16
+                   error("AdvDiff case $case: pass the wind in inputs[:b200_case_constants]")
+            phys[9:11] .= wind
+        elseif eqs == "ShallowWater"
+            case == "SoliWaveIsland" || error("ShallowWater case $case: pass the constants in inputs[:b200_case_constants]")
+            # user_flux.jl:44-86, user_source.jl:34-73: cone height, dry relaxation, g, film depth, cone centre and radius
+            phys[10:16] .= (0.93, 25.0, 9.81, 1.0e-3, 12.5, 0.0, 3.6)
+        end
+    end
+    return phys
+end
+
 "Build the device-resident problem from what params_setup returns (params_setup.jl:442-479)."
 function b200_setup(params, inputs; device = 0, rank = 0, nranks = 1, uid = C_NULL)
+    overlap = get(inputs, :b200_overlap, 0)
     ctx = Ref{Ctx}(C_NULL)
-    rc = ccall((:jx_init, LIB), Cint, (Cint, Cint, Cint, Ptr{Cvoid}, Ref{Ctx}), device, rank, nranks, uid, ctx)
-    rc == 0 || error("jx_init failed ($rc): no CUDA device / NCCL")
+    # jx_init_ex caps the NCCL communicator to `overlap` CTAs (ncclCommInitRankConfig), so the exchange kernels fit on the SMs
+    # the interface-first overlap leaves free -- no environment variables needed
+    rc = ccall((:jx_init_ex, LIB), Cint, (Cint, Cint, Cint, Ptr{Cvoid}, Cint, Ref{Ctx}), device, rank, nranks, uid,
+               nranks > 1 ? overlap : 0, ctx)
+    rc == 0 || error("jx_init_ex failed ($rc): no CUDA device / NCCL")
     c = ctx[]
     mesh, metrics, basis = params.mesh, params.metrics, params.basis
     nsd = mesh.nsd; ngl = mesh.ngl; neqs = params.neqs
-    PhysConst = params.PhysConst
-    phys = Float64[PhysConst.C0, PhysConst.γ, PhysConst.g, PhysConst.Rair, PhysConst.cp, PhysConst.cv,
-                   PhysConst.pref, PhysConst.γm1, 0.0, 0.0, 0.0]
+    phys = packed_constants(inputs)
     # engine options (include/jexrhs.h): inputs[:b200_dss] = :gather (deterministic, reference summation order, default)
     # or :atomics (throughput mode); the element kernel is chosen by the library (JX_ELEM_AUTO) unless
     # inputs[:b200_elem_kernel] names a variant; the shared jx_pow keeps the equation of state reproducible
     check(c, ccall((:jx_set_option, LIB), Cint, (Ctx, Cint, Int64), c, 1, get(inputs, :b200_dss, :gather) == :atomics ? 1 : 0))
     check(c, ccall((:jx_set_option, LIB), Cint, (Ctx, Cint, Int64), c, 2, get(inputs, :b200_pow, 1)))
     check(c, ccall((:jx_set_option, LIB), Cint, (Ctx, Cint, Int64), c, 3, get(inputs, :b200_elem_kernel, 0)))
-    # inputs[:b200_overlap] = n > 0 (atomics mode, several ranks): interface elements first, the NCCL exchange beside the
-    # interior launch with n SMs left to it; set ENV["NCCL_MAX_CTAS"] = ENV["NCCL_MAX_P2P_NCHANNELS"] = string(n) before
-    # jx_init so that the send/recv kernels fit on those SMs (JX_OPT_OVERLAP)
-    check(c, ccall((:jx_set_option, LIB), Cint, (Ctx, Cint, Int64), c, 5, get(inputs, :b200_overlap, 0)))
+    check(c, ccall((:jx_set_option, LIB), Cint, (Ctx, Cint, Int64), c, 5, overlap))
     μ = Float64.(params.visc_coeff)                                          # inputs[:μ], params_setup.jl:307-315
-    lpert = inputs[:SOL_VARS_TYPE] == PERT() ? 1 : 0
+    lpert = inputs[:SOL_VARS_TYPE] == J.PERT() ? 1 : 0
     check(c, ccall((:jx_set_problem, LIB), Cint,
                    (Ctx, Cint, Cint, Cint, Int64, Int64, Cint, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint),
-                   c, nsd, ngl, neqs, mesh.nelem, mesh.npoin, EQ_IDS[inputs[:equations]], lpert,
+                   c, nsd, ngl, neqs, mesh.nelem, mesh.npoin, equation_id(inputs), lpert,
                    inputs[:lsource] ? 1 : 0, inputs[:lvisc] ? 1 : 0, μ, phys, length(phys)))
     mets = nsd == 3 ?
         [metrics.dξdx, metrics.dξdy, metrics.dξdz, metrics.dηdx, metrics.dηdy, metrics.dηdz,
@@ -75,26 +124,51 @@ function b200_setup(params, inputs; device = 0, rank = 0, nranks = 1, uid = C_NU
         check(c, ccall((:jx_upload_bcs, LIB), Cint, (Ctx, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
                        c, size(mesh.poin_in_bdy_edge, 1), mesh.poin_in_bdy_edge, metrics.nx, metrics.ny, C_NULL, kinds))
     end
-    cache = params.g_dss_cache                                               # AssemblerCache, mpi_communications.jl:48-73
-    if cache !== nothing && nranks > 1
+    # AssemblerCache (mpi_communications.jl:48-73).  Uploaded whenever its lists are non-empty -- also on ONE rank, where
+    # periodic twins are summed by the reference's MPI self-send (mpi_communications.jl:99-112).
+    cache = params.g_dss_cache
+    if cache !== nothing && any(!isempty, cache.send_i)
         csr(v) = (Int64[0; cumsum(length.(v))], Int64.(reduce(vcat, v; init = Int64[])))
         sp, sv = csr(cache.send_i); rp, rv = csr(cache.recv_idx_buffers); bp, bv = csr(cache.recvback_idx_buffers)
         check(c, ccall((:jx_upload_halo, LIB), Cint, (Ctx, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
                        c, sp, sv, rp, rv, bp, bv))
     end
-    return c
+    return B200Params(params, c, Vector{Float64}(undef, mesh.npoin * neqs))
 end
 
-"Same signature and semantics as rhs!(du,u,params,time) (rhs.jl:121-134): in place, returns nothing, mutates u."
-function rhs_b200!(du, u, params, time)
-    c = params.b200ctx
-    check(c, ccall((:jx_rhs, LIB), Cint, (Ctx, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), c, time, u, du, u))
+"""
+Same signature and semantics as rhs!(du,u,params,time) (rhs.jl:121-134): in place, returns nothing, mutates u.
+`du` may be the ArrayFuse of OrdinaryDiffEq's low-storage methods (CarpenterKennedy2N54 with its default
+`williamson_condition = true`; rhs.jl:14-27), which has no pointer and only scalar `setindex!`: then the result goes through
+a host buffer and is stored element by element exactly like RHStoDU!, so the fused stage update still happens in the store.
+"""
+function rhs_b200!(du, u, p::B200Params, time)
+    c = p.ctx
+    if du isa Array{Float64}
+        check(c, ccall((:jx_rhs, LIB), Cint, (Ctx, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), c, time, u, du, u))
+    else
+        buf = p.dubuf
+        check(c, ccall((:jx_rhs, LIB), Cint, (Ctx, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), c, time, u, buf, u))
+        @inbounds for i in eachindex(buf)
+            du[i] = buf[i]
+        end
+    end
+    return nothing
+end
+
+"""
+rhs! on a device-resident state (`u`, `du` CuArray{Float64} on the context's device): no PCIe copy; `pointer(::CuArray)`
+is a CuPtr whose bits are the device address jx_rhs_dev expects.
+"""
+function rhs_b200_dev!(du, u, p::B200Params, time)
+    up = reinterpret(Ptr{Float64}, UInt(pointer(u))); dp = reinterpret(Ptr{Float64}, UInt(pointer(du)))
+    check(p.ctx, ccall((:jx_rhs_dev, LIB), Cint, (Ctx, Float64, Ptr{Float64}, Ptr{Float64}), p.ctx, time, up, dp))
     return nothing
 end
 
 "Replaces solve(prob, alg; dt, adaptive=false) for the fixed-step explicit schemes: all stages on the device."
-function step_b200!(u, params, inputs, t, nsteps)
-    c = params.b200ctx
+function step_b200!(u, p::B200Params, inputs, t, nsteps)
+    c = p.ctx
     dt = Float64(Float32(inputs[:Δt]))                                        # TimeIntegrators.jl:464-465
     check(c, ccall((:jx_set_state, LIB), Cint, (Ctx, Ptr{Float64}), c, u))
     check(c, ccall((:jx_step, LIB), Cint, (Ctx, Cint, Float64, Float64, Cint), c, SCHEMES[string(nameof(typeof(inputs[:ode_solver])))], t, dt, nsteps))
@@ -102,6 +176,6 @@ function step_b200!(u, params, inputs, t, nsteps)
     return t + nsteps * dt
 end
 
-b200_free(c::Ctx) = ccall((:jx_destroy, LIB), Cvoid, (Ctx,), c)
+b200_free(p::B200Params) = ccall((:jx_destroy, LIB), Cvoid, (Ctx,), p.ctx)
 
 end # module

@@ -253,21 +253,17 @@ def test_device_built_metrics_bit_exact(nsd, nop):
         assert np.array_equal(du2, dus[0]), rel_err_per_node(du2, dus[0])
 
 
-# ---- pencil element kernel (JX_OPT_ELEM_KERNEL 1 = exact order, 2 = single partial) ---------------
-@pytest.mark.parametrize("variant", [1, 3, 5, 6, 8, 9])
-@pytest.mark.parametrize("nop", [2, 4, 5])
+# ---- warp-team element kernels (JX_OPT_ELEM_KERNEL 8 / 9: k_elem_team; 10 / 11: k_elem_team2) ----------------
+@pytest.mark.parametrize("variant", [8, 9])
+@pytest.mark.parametrize("nop", [2, 4])
 @pytest.mark.parametrize("lpert", [False, True])
-def test_pencil_kernel_bit_exact(variant, nop, lpert):
-    """Variants 1, 3, 5, 6 re-tile the work (one thread per LGL line and direction; 3 = one element per
-    CTA; 5 = pencils of an element group flattened over the CTA's lanes, 6 = the same with one element;
-    8/9 = plane-role + zeta-role warp team)
-    but keep the reference's left-to-right order of every sum, so they must reproduce the oracle bit for
-    bit.  The 5x4x3-element box is not a multiple of the group sizes (5, 7): ragged last group."""
-    if variant in (1, 5, 8) and nop >= 5:
-        pytest.skip("variants 1, 5 and 8 are instantiated for nop 2 and 4")
-    if variant in (6, 9) and nop != 4:
-        pytest.skip("variants 6 and 9 are instantiated for nop 4")
-    spec = box3d((5, 4, 3) if nop < 7 else (3, 2, 2), nop, warp=0.05)
+def test_team_kernel_bit_exact(variant, nop, lpert):
+    """Plane-role + zeta-role warp team (8: one plane warp, 9: two): the work is re-tiled but every sum keeps the
+    reference's left-to-right order, so the oracle must be reproduced bit for bit.  The 5x3x3-element box leaves a ragged
+    last group for both group sizes (3 elements at nop 2, 2 at nop 4)."""
+    if variant == 9 and nop != 4:
+        pytest.skip("variant 9 is instantiated for nop 4")
+    spec = box3d((5, 3, 3), nop, warp=0.05)
     sems, qns, qes, us = euler_case(spec, 1, lpert=lpert)
     dus, ub, _ = _oracle_rhs(sems, qes, us, lpert, False, pow_mode=1)
     du, u = _gpu_rhs(sems, qes, us, lpert, False, pow_mode=1, dss_mode=0, elem_kernel=variant)
@@ -275,54 +271,111 @@ def test_pencil_kernel_bit_exact(variant, nop, lpert):
     assert np.array_equal(du, dus[0]), rel_err_per_node(du, dus[0])
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 8, 9])
+@pytest.mark.parametrize("variant", [8, 9, 11])
 @pytest.mark.parametrize("lpert", [False, True])
-def test_pencil_kernel_atomics(variant, lpert):
-    """The bench configuration: pencil kernel + atomics DSS with M^-1 folded in; <= 1e-12 per node,
-    <= 1e-10 relative L2 (north-star bars; slack covers summation order)."""
-    spec = box3d((7, 6, 3), 4, warp=0.05)      # 126 elements: ragged last group of 5
+def test_team_kernel_atomics(variant, lpert):
+    """The bench configuration: team kernel + atomics DSS with M^-1 folded in; <= 1e-12 per node, <= 1e-10 relative L2
+    (north-star bars; the slack covers the unordered DSS sum)."""
+    if variant == 11 and lpert:
+        pytest.skip("k_elem_team2 is instantiated for TOTAL")
+    spec = box3d((7, 5, 3), 4, warp=0.05)      # 105 elements: ragged last pair
     sems, qns, qes, us = euler_case(spec, 1, lpert=lpert)
     dus, ub, _ = _oracle_rhs(sems, qes, us, lpert, False, pow_mode=1)
     du, u = _gpu_rhs(sems, qes, us, lpert, False, pow_mode=1, dss_mode=1, elem_kernel=variant)
     N = sems[0].mesh.npoin
-    # variants 2/4 associate the nine metric products differently (one partial instead of three): measured
-    # 3e-12 per node on the near-zero horizontal momenta, outside the 1e-12 bar -- they are opt-in, not default
-    bar = 1e-12 if variant in (1, 3, 5, 6, 8, 9) else 1e-10
     for e in range(5):
         pn, l2 = rel_err_per_node(du[e * N:(e + 1) * N], dus[0][e * N:(e + 1) * N])
-        assert pn <= bar and l2 <= 1e-10, (variant, lpert, e, pn, l2)
+        assert pn <= 1e-12 and l2 <= 1e-10, (variant, lpert, e, pn, l2)
 
 
-@pytest.mark.parametrize("nel", [(5, 3, 3), (13, 11, 9), (21, 19, 21)])
-def test_team2_kernel_bit_exact(nel):
-    """k_elem_team2 (variant 10: node image + TMA row gathers, ring of equation slots, producer/consumer barriers):
-    same order of every sum as the reference, so bit-exact against the oracle.  Odd element counts leave a ragged last
-    pair; 8379 elements give every CTA of the persistent grid (148 SMs x 4) seven pairs, so the slot ring goes once
-    round and the two-buffer hand-shakes wrap many times."""
-    spec = box3d(nel, 4, warp=0.05)
-    sems, qns, qes, us = euler_case(spec, 1, lpert=False)
-    dus, ub, _ = _oracle_rhs(sems, qes, us, False, False, pow_mode=1)
-    du, u = _gpu_rhs(sems, qes, us, False, False, pow_mode=1, dss_mode=0, elem_kernel=10)
+@pytest.mark.parametrize("lpert", [False, True])
+@pytest.mark.parametrize("mu", [MU3, [0.0, 125.0, 0.0, 60.0, 125.0], [5.0, 125.0, 125.0, 125.0, 125.0]])
+def test_visc_team_kernel_bit_exact(lpert, mu):
+    """k_visc_team: the AV viscous term of 3D nop-4 elements as a warp-team pass of its own (line owners with all nine metric
+    terms of their nodes, metric-free plane lanes) behind the inviscid team kernel; same order of every sum as the reference.
+    1287 elements: ragged last pair, several pairs per CTA.  The mu vectors exercise the skipping of inviscid equations
+    (4, 3 and 5 viscous equations: uneven halves)."""
+    spec = box3d((13, 11, 9), 4, warp=0.05)
+    sems, qns, qes, us = euler_case(spec, 1, lpert=lpert)
+    probs = [ref.RefProblem(sems[0], qes[0], eq_id=0, lpert=lpert, lsource=True, lvisc=True, visc_coeff=mu, phys=PHYS, pow_mode=1)]
+    run = ref.RefRun(probs, None)
+    ub, dus = [us[0].copy()], [np.zeros_like(us[0])]
+    run.rhs(dus, ub, 0.0)
+    inputs = dict(_inputs(lpert, True, 3), mu=mu)
+    for dss in (0, 1):
+        p = jrhs.params_setup(sems[0], qes[0], inputs, pow_mode=1, dss_mode=dss, elem_kernel=9)
+        try:
+            u, du = us[0].copy(), np.empty_like(us[0])
+            jrhs.rhs_bang(du, u, p, 0.0)
+        finally:
+            p.close()
+        assert np.array_equal(u, ub[0])
+        if dss == 0:
+            assert np.array_equal(du, dus[0]), rel_err_per_node(du, dus[0])
+        else:
+            N = sems[0].mesh.npoin
+            for e in range(5):
+                pn, l2 = rel_err_per_node(du[e * N:(e + 1) * N], dus[0][e * N:(e + 1) * N])
+                assert pn <= 1e-12 and l2 <= 1e-10, (e, pn, l2)
+
+
+@pytest.mark.parametrize("lpert", [False, True])
+def test_tri_kernel_nop7_bit_exact(lpert):
+    """k_elem_tri (variant 12, nop 7): xi-, eta- and zeta-pencil roles on XOR-swizzled tiles, same order of every sum as the
+    reference.  343 elements give the CTAs of the persistent grid (148 SMs x 2) more than one element each."""
+    spec = box3d((7, 7, 7), 7, warp=0.05)
+    sems, qns, qes, us = euler_case(spec, 1, lpert=lpert)
+    dus, ub, _ = _oracle_rhs(sems, qes, us, lpert, False, pow_mode=1)
+    du, u = _gpu_rhs(sems, qes, us, lpert, False, pow_mode=1, dss_mode=0, elem_kernel=12)
     assert np.array_equal(u, ub[0])
     assert np.array_equal(du, dus[0]), rel_err_per_node(du, dus[0])
-    # the bench configuration: RED.ADD scatter with M^-1 folded into the weight
-    du, u = _gpu_rhs(sems, qes, us, False, False, pow_mode=1, dss_mode=1, elem_kernel=10)
+    du, u = _gpu_rhs(sems, qes, us, lpert, False, pow_mode=1, dss_mode=1, elem_kernel=12)
     N = sems[0].mesh.npoin
     for e in range(5):
         pn, l2 = rel_err_per_node(du[e * N:(e + 1) * N], dus[0][e * N:(e + 1) * N])
         assert pn <= 1e-12 and l2 <= 1e-10, (e, pn, l2)
 
 
-def test_pencil_kernel_requires_layout_before_upload():
-    """Variant 1/2 read a different element-record layout: switching after the upload is refused."""
+@pytest.mark.parametrize("variant", [10, 11])
+@pytest.mark.parametrize("nel", [(5, 3, 3), (13, 11, 9), (21, 19, 21)])
+def test_team2_kernel_bit_exact(nel, variant):
+    """k_elem_team2 (variants 10 / 11: node image + TMA row gathers, ring of equation slots, producer/consumer barriers;
+    10 lands the rows in dead ring slots, 11 in a dedicated tile):
+    same order of every sum as the reference, so bit-exact against the oracle.  Odd element counts leave a ragged last
+    pair; 8379 elements give every CTA of the persistent grid (148 SMs x 4) seven pairs, so the slot ring goes once
+    round and the two-buffer hand-shakes wrap many times."""
+    spec = box3d(nel, 4, warp=0.05)
+    sems, qns, qes, us = euler_case(spec, 1, lpert=False)
+    dus, ub, _ = _oracle_rhs(sems, qes, us, False, False, pow_mode=1)
+    du, u = _gpu_rhs(sems, qes, us, False, False, pow_mode=1, dss_mode=0, elem_kernel=variant)
+    assert np.array_equal(u, ub[0])
+    assert np.array_equal(du, dus[0]), rel_err_per_node(du, dus[0])
+    # the bench configuration: RED.ADD scatter with M^-1 folded into the weight
+    du, u = _gpu_rhs(sems, qes, us, False, False, pow_mode=1, dss_mode=1, elem_kernel=variant)
+    N = sems[0].mesh.npoin
+    for e in range(5):
+        pn, l2 = rel_err_per_node(du[e * N:(e + 1) * N], dus[0][e * N:(e + 1) * N])
+        assert pn <= 1e-12 and l2 <= 1e-10, (e, pn, l2)
+
+
+def test_kernel_variant_requires_its_record_layout_before_upload():
+    """k_elem_team2 (variants 10/11) reads pair records extended by the row-run tables (layout 6), and the generic kernel
+    per-element records (layout 0): switching to a kernel of another layout after the upload is refused with JX_ESTATE,
+    a variant that is not compiled with JX_EINVAL, and the context keeps working with the kernel it had."""
     from jexpresso_b200 import capi
     spec = box3d((3, 3, 3), 4)
     sems, qns, qes, us = euler_case(spec, 1, lpert=False)
     p = jrhs.params_setup(sems[0], qes[0], _inputs(False, False, 3), pow_mode=1, dss_mode=0, elem_kernel=0)
     try:
         with pytest.raises(capi.JexError) as ei:
-            p.ctx.set_option(capi.JX_OPT_ELEM_KERNEL, 1)
+            p.ctx.set_option(capi.JX_OPT_ELEM_KERNEL, 10)
         assert ei.value.code == capi.JX_ESTATE
+        with pytest.raises(capi.JexError) as ei:
+            p.ctx.set_option(capi.JX_OPT_ELEM_KERNEL, 3)        # a round-1 pencil variant: no longer compiled
+        assert ei.value.code == capi.JX_EINVAL
+        u, du = us[0].copy(), np.empty_like(us[0])
+        jrhs.rhs_bang(du, u, p, 0.0)
+        assert np.isfinite(du).all()
     finally:
         p.close()
 
