@@ -8,6 +8,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -116,11 +118,12 @@ struct jx_ctx {
     // device arrays
     double *u = nullptr, *du = nullptr, *tmp = nullptr, *qe = nullptr, *Minv = nullptr, *coords = nullptr;
     double *rhs_el = nullptr, *rhs_el_visc = nullptr;
-    double *aux = nullptr;           // per-node flux ingredient (k_node_aux) or node image (k_node_image)
+    double *aux = nullptr;           // per-node flux ingredient (k_node_aux)
     size_t aux_doubles = 0;
-    double row_runs_per_elem = 0.0;  // k_elem_team2: bulk copies per element after merging consecutive node ids
+    bool aux_fresh = false;          // k_stage_fused left aux = aux(c->u) and c->du zeroed: the next rhs_core(c->u, c->du) skips k_node_aux
     char *rec = nullptr;
     char *rec_visc = nullptr;        // pair records of the viscous pass (k_visc_team), lvisc only
+    int32_t *d_eorig = nullptr;      // team records: position -> element id (order_elements); nullptr = identity
     int64_t *n2e_ptr = nullptr;
     uint32_t *n2e_idx = nullptr;
     double dpsi[64] = {0};
@@ -235,7 +238,7 @@ void free_split(jx_ctx *c) {
 void free_mesh(jx_ctx *c) {
     free_split(c);
     dfree(c->u); dfree(c->du); dfree(c->tmp); dfree(c->qe); dfree(c->Minv); dfree(c->coords);
-    dfree(c->rhs_el); dfree(c->rhs_el_visc); dfree(c->aux); c->aux_doubles = 0; dfree(c->rec); dfree(c->rec_visc); dfree(c->n2e_ptr); dfree(c->n2e_idx);
+    dfree(c->rhs_el); dfree(c->rhs_el_visc); dfree(c->aux); c->aux_doubles = 0; dfree(c->rec); dfree(c->rec_visc); dfree(c->d_eorig); dfree(c->n2e_ptr); dfree(c->n2e_idx);
     for (auto &p : c->ss) dfree(p);
     c->have_mesh = false;
     c->rec_layout = -1;
@@ -263,7 +266,8 @@ int select_kernels(jx_ctx *c) {
     if (c->elem_variant == JX_ELEM_AUTO) {
         // fastest exact-order kernel that exists for this configuration: the warp-team kernels (bit-identical to the
         // generic one), else the generic thread-per-node kernel.  Resident records pin the choice to their layout.
-        const int order[] = {12, 9, 8, 0};   // 12: nop 7, 9/8: nop 4/2 (10/11 = k_elem_team2, opt-in: profiles/r02b)
+        // 9/8: nop 4/2.  Opt-in only: 12 (k_elem_tri, nop 7: 23.8 GDOF/s against 27.5 for the generic kernel, profiles/r02c)
+        const int order[] = {9, 8, 0};
         for (int v : order) {
             ks = lookup(v);
             if (ks && (!c->have_mesh || ks->rec_layout == c->rec_layout)) break;
@@ -369,6 +373,7 @@ extern "C" int jx_last_error(jx_ctx *c, char *buf, int len) {
 
 extern "C" int jx_set_option(jx_ctx *c, int key, int64_t value) {
     if (!c) return JX_EINVAL;
+    if (key != JX_OPT_CUDA_GRAPH) c->aux_fresh = false;
     const int old_dss = c->dss_mode, old_pow = c->pow_mode, old_var = c->elem_variant;
     switch (key) {
         case JX_OPT_DSS_MODE:
@@ -404,6 +409,7 @@ extern "C" int jx_set_problem(jx_ctx *c, int nsd, int ngl, int neqs, int64_t nel
         return fail(c, JX_EINVAL, "jx_set_problem: bad dimensions");
     if (npoin >= (int64_t)1 << 31) return fail(c, JX_EINVAL, "npoin must be < 2^31 per rank");
     cudaSetDevice(c->device);
+    c->aux_fresh = false;
     free_mesh(c); free_bcs(c); free_halo(c);
     c->nsd = nsd; c->ngl = ngl; c->neqs = neqs; c->nelem = nelem; c->npoin = npoin;
     c->eq_id = equation_id; c->lpert = lpert ? 1 : 0; c->lsource = lsource ? 1 : 0; c->lvisc = lvisc ? 1 : 0;
@@ -424,41 +430,61 @@ extern "C" int jx_set_problem(jx_ctx *c, int nsd, int ngl, int neqs, int64_t nel
 // ------------------------------------------------------------------------------------------
 namespace {
 
-// Row-run tables of the pair records (k_elem_team2).  Per element: its node ids in ascending order are the rows of its
-// node-image tile; wpos[n] = row of flux-view node n; consecutive ids form one run = one bulk copy.  With the
-// reference's numbering (vertices, then the interior nodes of every edge, face and volume as contiguous blocks,
-// mesh.jl:4084+, 4555+, 4944+) a hexahedron of order 4 has at most 27 runs instead of 125 single rows.
-int build_row_runs(jx_ctx *c, const int64_t *connijk) {
-    const KernelSet *ks = c->ks;
+// Record order of the team kernels: elements sorted along a Morton curve through their centres (cells of one mean element
+// size), so that the elements a CTA wave works on share faces, edges and vertices -- their q / aux gathers and du RED.ADDs
+// then hit L2 instead of DRAM (x-fastest order of a 73^3 box: the z-neighbour comes 5329 elements = 75 MB of records
+// later; measured L2 hit rate 38 %, profiles/r01g).  Pure data placement: every element keeps its arithmetic, rhs_el keeps
+// the caller's numbering (ElemArgs::eorig) and the deterministic gather its element-ascending order.
+// JX_ELEM_ORDER=0 in the environment keeps the caller's order.
+int order_elements(jx_ctx *c, const int64_t *connijk, const double *coords, std::vector<int32_t> &epos) {
     const int64_t E = c->nelem;
-    const int np = c->np, epb = ks->elems_per_block, maxrun = ks->maxrun;
-    const int64_t ngroups = (E + epb - 1) / epb;
-    const size_t ext = (size_t)ks->group_bytes - ks->wpos_off;
-    std::vector<unsigned char> tab((size_t)ngroups * ext, 0);
-    std::vector<std::pair<int64_t, int>> ids((size_t)np);
-    int64_t total_runs = 0;
+    const int np = c->np, nsd = c->nsd;
+    epos.clear();
+    const char *env = getenv("JX_ELEM_ORDER");
+    if (!coords || E < 2 || (env && env[0] == '0')) return JX_OK;
+    std::vector<double> cen((size_t)E * 3, 0.0);
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int64_t iel = 0; iel < E; ++iel) {
-        const int64_t g = iel / epb;
-        const int s = (int)(iel % epb);
-        unsigned char *rec = tab.data() + (size_t)g * ext;
-        unsigned char *wpos = rec;
-        int32_t *runi = reinterpret_cast<int32_t *>(rec + (ks->runi_off - ks->wpos_off)) + (size_t)s * maxrun;
-        unsigned char *runr = rec + (ks->runr_off - ks->wpos_off) + (size_t)s * maxrun;
-        unsigned char *runl = rec + (ks->runl_off - ks->wpos_off) + (size_t)s * maxrun;
-        int32_t *nrun = reinterpret_cast<int32_t *>(rec + (ks->nrun_off - ks->wpos_off));
-        for (int l = 0; l < np; ++l) ids[l] = {connijk[(size_t)iel + (size_t)E * l] - 1, l};
-        std::sort(ids.begin(), ids.end());
-        int nr = 0;
-        for (int r = 0; r < np; ++r) {
-            wpos[s * np + ids[r].second] = (unsigned char)r;
-            if (r > 0 && ids[r].first == ids[r - 1].first + 1 && runl[nr - 1] < 255) runl[nr - 1]++;
-            else { runi[nr] = (int32_t)ids[r].first; runr[nr] = (unsigned char)r; runl[nr] = 1; ++nr; }
+        const int64_t a = connijk[(size_t)iel] - 1, b = connijk[(size_t)iel + (size_t)E * (np - 1)] - 1;   // opposite corners
+        if (a < 0 || a >= c->npoin || b < 0 || b >= c->npoin) return JX_OK;                                 // reported by the CSR build
+        for (int d = 0; d < nsd; ++d) {
+            const double x = 0.5 * (coords[(size_t)a * nsd + d] + coords[(size_t)b * nsd + d]);
+            cen[(size_t)iel * 3 + d] = x;
+            lo[d] = std::min(lo[d], x); hi[d] = std::max(hi[d], x);
         }
-        nrun[s] = nr;
-        total_runs += nr;
     }
-    c->row_runs_per_elem = E > 0 ? (double)total_runs / (double)E : 0.0;
-    CK(cudaMemcpy2D(c->rec + ks->wpos_off, (size_t)ks->group_bytes, tab.data(), ext, ext, (size_t)ngroups, cudaMemcpyHostToDevice));
+    double vol = 1.0;
+    int dims = 0;
+    for (int d = 0; d < nsd; ++d)
+        if (hi[d] > lo[d]) { vol *= hi[d] - lo[d]; ++dims; }
+    if (dims == 0) return JX_OK;
+    const double h = std::pow(vol / (double)E, 1.0 / dims);
+    if (!(h > 0.0) || !std::isfinite(h)) return JX_OK;
+    auto spread = [](uint64_t v) {   // 21 bits -> every third bit
+        v &= 0x1fffffull;
+        v = (v | v << 32) & 0x1f00000000ffffull;
+        v = (v | v << 16) & 0x1f0000ff0000ffull;
+        v = (v | v << 8) & 0x100f00f00f00f00full;
+        v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+        v = (v | v << 2) & 0x1249249249249249ull;
+        return v;
+    };
+    std::vector<std::pair<uint64_t, int32_t>> key((size_t)E);
+    for (int64_t iel = 0; iel < E; ++iel) {
+        uint64_t k = 0;
+        for (int d = 0; d < nsd; ++d) {
+            const double q = (cen[(size_t)iel * 3 + d] - lo[d]) / h;
+            k |= spread((uint64_t)std::min(q < 0 ? 0.0 : q, 2097151.0)) << d;
+        }
+        key[(size_t)iel] = {k, (int32_t)iel};
+    }
+    std::sort(key.begin(), key.end());
+    epos.resize((size_t)E);
+    std::vector<int32_t> eorig((size_t)E);
+    for (int64_t p = 0; p < E; ++p) { eorig[(size_t)p] = key[(size_t)p].second; epos[(size_t)key[(size_t)p].second] = (int32_t)p; }
+    int rc = dalloc(c, &c->d_eorig, (size_t)E);
+    if (rc) return rc;
+    CK(cudaMemcpy(c->d_eorig, eorig.data(), (size_t)E * 4, cudaMemcpyHostToDevice));
     return JX_OK;
 }
 
@@ -472,7 +498,7 @@ int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, co
     const int64_t total = E * np;
     const size_t nq = (size_t)N * q;
     const bool tri = c->ks->rec_layout == 7;          // per-element pencil-stream records of k_elem_tri
-    const bool grouped = c->ks->rec_layout == 5 || c->ks->rec_layout == 6;   // element-group records of the team kernels (6: + row-run tables)
+    const bool grouped = c->ks->rec_layout == 5;   // element-group records of the team kernels
     const int64_t ngroups = grouped ? (E + c->ks->elems_per_block - 1) / c->ks->elems_per_block : 0;
     const size_t rec_total = grouped ? (size_t)ngroups * c->ks->group_bytes : (tri ? (size_t)E * c->ks->group_bytes : (size_t)E * c->rec_bytes);
     int rc;
@@ -492,12 +518,12 @@ int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, co
     // staging buffer reused for every element-sized host array
     double *d_stage = nullptr, *d_omega = nullptr, *d_dpsi = nullptr;
     int64_t *d_conn = nullptr;
-    int32_t *d_cnt = nullptr;
+    int32_t *d_cnt = nullptr, *d_epos = nullptr;
     if ((rc = dalloc(c, &d_stage, (size_t)std::max<int64_t>(total, N * c->nsd))) || (rc = dalloc(c, &d_omega, (size_t)c->ngl)) ||
         (rc = dalloc(c, &d_dpsi, (size_t)c->ngl * c->ngl)) || (rc = dalloc(c, &d_conn, (size_t)total)) ||
         (rc = dalloc(c, &d_cnt, (size_t)N)))
         return rc;
-    auto cleanup = [&]() { dfree(d_stage); dfree(d_omega); dfree(d_dpsi); dfree(d_conn); dfree(d_cnt); };
+    auto cleanup = [&]() { dfree(d_stage); dfree(d_omega); dfree(d_dpsi); dfree(d_conn); dfree(d_cnt); dfree(d_epos); };
 #define CKC(call)                                                                                    \
     do {                                                                                             \
         cudaError_t e_ = (call);                                                                     \
@@ -551,10 +577,17 @@ int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, co
         c->launches += c->nmet + 2;
     } else if (total > 0 && grouped) {
         const KernelSet *ks = c->ks;
+        std::vector<int32_t> epos;
+        if ((rc = order_elements(c, connijk, coords, epos))) { cleanup(); return rc; }
+        if (!epos.empty()) {
+            if ((rc = dalloc(c, &d_epos, (size_t)E))) { cleanup(); return rc; }
+            CKC(cudaMemcpyAsync(d_epos, epos.data(), (size_t)E * 4, cudaMemcpyHostToDevice, c->stream));
+            CKC(cudaStreamSynchronize(c->stream));
+        }
         GroupRetileArgs ga;
-        ga.src = nullptr; ga.omega = d_omega; ga.Minv = c->Minv; ga.connijk = d_conn; ga.rec = c->rec; ga.nelem = E;
+        ga.src = nullptr; ga.omega = d_omega; ga.Minv = c->Minv; ga.connijk = d_conn; ga.epos = d_epos; ga.rec = c->rec; ga.nelem = E;
         ga.ngl = c->ngl; ga.epb = ks->elems_per_block; ga.group_bytes = ks->group_bytes;
-        ga.zid_off = ks->zid_off; ga.fid_off = ks->fid_off; ga.z_off = ks->z_off;
+        ga.zid_off = ks->zid_off; ga.fid_off = ks->fid_off; ga.z_off = ks->z_off; ga.w_off = ks->w_off; ga.wf_off = ks->wf_off;
         CKC(cudaMemsetAsync(c->rec, 0, rec_total, c->stream));
         ga.slot = -1;
         k_retile_group<<<nblk(total, 256), 256, 0, c->stream>>>(ga);
@@ -564,8 +597,8 @@ int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, co
             const size_t vbytes = (size_t)ngroups * ks->visc_group_bytes;
             if ((rc = dalloc(c, &c->rec_visc, vbytes))) { cleanup(); return rc; }
             CKC(cudaMemsetAsync(c->rec_visc, 0, vbytes, c->stream));
-            vr.src = nullptr; vr.omega = d_omega; vr.Minv = c->Minv; vr.connijk = d_conn; vr.rec = c->rec_visc; vr.nelem = E;
-            vr.ngl = c->ngl; vr.epb = ks->elems_per_block; vr.group_bytes = ks->visc_group_bytes; vr.zslot_bytes = ks->visc_zslot_bytes;
+            vr.src = nullptr; vr.omega = d_omega; vr.Minv = c->Minv; vr.connijk = d_conn; vr.epos = d_epos; vr.rec = c->rec_visc; vr.nelem = E;
+            vr.ngl = c->ngl; vr.epb = ks->elems_per_block; vr.group_bytes = ks->visc_group_bytes;
             vr.zid_off = ks->visc_zid_off; vr.fid_off = ks->visc_fid_off;
             vr.slot = -1;
             k_retile_visc<<<nblk(total, 256), 256, 0, c->stream>>>(vr);
@@ -588,11 +621,6 @@ int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, co
             k_retile_visc<<<nblk(total, 256), 256, 0, c->stream>>>(vr);
         }
         c->launches += (c->nmet + 2) * (with_visc ? 2 : 1);
-        if (ks->maxrun > 0) {
-            CKC(cudaStreamSynchronize(c->stream));
-            const int rr = build_row_runs(c, connijk);
-            if (rr) { cleanup(); return rr; }
-        }
     } else if (total > 0) {
         CKC(cudaMemsetAsync(c->rec, 0, rec_total, c->stream));
         ra.slot = -1;
@@ -630,6 +658,7 @@ int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, co
     cleanup();
 #undef CKC
     c->have_mesh = true;
+    c->aux_fresh = false;
     c->rec_layout = c->ks->rec_layout;
     return JX_OK;
 }
@@ -769,6 +798,7 @@ extern "C" int jx_set_state(jx_ctx *c, const double *u) {
     if (!c || !u) return JX_EINVAL;
     if (!c->have_mesh) return fail(c, JX_ESTATE, "jx_set_state before jx_upload_mesh");
     cudaSetDevice(c->device);
+    c->aux_fresh = false;
     CK(cudaMemcpyAsync(c->u, u, (size_t)c->npoin * c->neqs * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return JX_OK;
@@ -888,7 +918,7 @@ int ensure_split(jx_ctx *c) {
     for (int64_t g = 0; g < ngroups; ++g) if (!flag[g]) list.push_back((int32_t)g);
     if (ni == 0 || ni == ngroups) return JX_OK;              // nothing to overlap with
     if ((rc = dalloc(c, &c->d_glist, (size_t)ngroups))) return rc;
-    if (!c->d_gctr && (rc = dalloc(c, &c->d_gctr, 2))) return rc;
+    if (!c->d_gctr && (rc = dalloc(c, &c->d_gctr, 4))) return rc;
     CK(cudaMemcpy(c->d_glist, list.data(), (size_t)ngroups * 4, cudaMemcpyHostToDevice));
     if (!c->stream2) {
         int least = 0, greatest = 0;
@@ -920,14 +950,32 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     cudaStream_t s = c->stream;
     const int64_t N = c->npoin, E = c->nelem;
     const int q = c->neqs;
+    const bool atomics = c->dss_mode == 1;
+    // the previous stage's fused update already zeroed du and evaluated aux on this state (k_stage_fused)
+    const bool own_state = atomics && u == c->u && du == c->du && ks->launch_aux && ks->launch_stage;
+    const bool fresh = c->aux_fresh && own_state && c->aux;
+    c->aux_fresh = false;
     if (c->nb > 0) {                                                     // rhs.jl:558
         PhaseScope ps(c, PH_BC);
         BcArgs b;
         b.u = u; b.qe = c->qe; b.node = c->bc_node; b.ptr = c->bc_ptr; b.normal = c->bc_normal; b.npoin = N; b.nb = c->nb;
+        b.aux = fresh ? c->aux : nullptr; b.phys = c->phys;
         ks->launch_bc(b, s);
         c->launches++;
     }
-    const bool atomics = c->dss_mode == 1;
+    auto stage_update = [&]() {
+        PhaseScope ps(c, PH_UPDATE);
+        if (own_state && c->aux) {
+            StageArgs sa;
+            sa.u = u; sa.tmp = c->tmp; sa.du = du; sa.qe = c->qe; sa.aux = c->aux; sa.npoin = N;
+            sa.A = upd.A; sa.B = upd.B; sa.dt = upd.dt; sa.first = upd.first; sa.phys = c->phys;
+            ks->launch_stage(sa, (int)std::min<int64_t>((N + 255) / 256, (int64_t)c->num_sms * 8), s);
+            c->aux_fresh = true;
+        } else {
+            k_lsrk_update<<<nblk(N * q, 256), 256, 0, s>>>(u, c->tmp, du, N * q, upd.A, upd.B, upd.dt, upd.first);
+        }
+        c->launches++;
+    };
     if (!atomics && (!c->rhs_el || (c->lvisc && !c->rhs_el_visc))) {
         int rc;
         if (!c->rhs_el && (rc = dalloc(c, &c->rhs_el, (size_t)E * c->np * q))) return rc;
@@ -938,7 +986,7 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     }
     ElemArgs ea;
     ea.u = u; ea.qe = c->qe; ea.rec = c->rec; ea.rhs_el = c->rhs_el; ea.rhs_el_visc = c->rhs_el_visc; ea.du = du;
-    ea.Minv = c->Minv; ea.coords = c->coords; ea.elist = nullptr; ea.nelem = E; ea.npoin = N;
+    ea.Minv = c->Minv; ea.coords = c->coords; ea.elist = nullptr; ea.eorig = c->d_eorig; ea.nelem = E; ea.npoin = N;
     ea.atomics = atomics ? 1 : 0; ea.lsource = c->lsource; ea.phys = c->phys;
     for (int i = 0; i < 8; ++i) ea.visc[i] = c->visc[i];
     for (int i = 0; i < 64; ++i) ea.dpsi[i] = c->dpsi[i];
@@ -948,42 +996,32 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     // pass over du.  The deterministic mode keeps the reference order (exchange, then divide_by_mass_matrix!).
     const bool fold_minv = atomics;
     ea.aux = nullptr;
-    if (ks->launch_image) {                                              // node image rows (+ zero-fill of du)
-        PhaseScope ps(c, PH_AUX);
-        if (!c->aux || c->aux_doubles < (size_t)N * ks->img_rowd) {
-            int rc = dalloc(c, &c->aux, (size_t)N * ks->img_rowd);
-            if (rc) return rc;
-            c->aux_doubles = (size_t)N * ks->img_rowd;
+    if (ks->launch_aux) {                                                // per-node flux ingredient (+ zero-fill of du)
+        if (!fresh) {
+            PhaseScope ps(c, PH_AUX);
+            if (!c->aux || c->aux_doubles < (size_t)N * 4) {                 // up to 4 values per node
+                int rc = dalloc(c, &c->aux, (size_t)N * 4);
+                if (rc) return rc;
+                c->aux_doubles = (size_t)N * 4;
+            }
+            AuxArgs aa;
+            aa.u = u; aa.qe = c->qe; aa.aux = c->aux; aa.zero = atomics ? du : nullptr; aa.npoin = N; aa.phys = c->phys;
+            ks->launch_aux(aa, (int)std::min<int64_t>((N + 255) / 256, (int64_t)c->num_sms * 8), s);
+            c->launches++;
         }
-        ImageArgs ia;
-        ia.u = u; ia.qe = c->qe; ia.img = c->aux; ia.zero = atomics ? du : nullptr; ia.npoin = N; ia.rowd = ks->img_rowd; ia.phys = c->phys;
-        ks->launch_image(ia, (int)std::min<int64_t>((N + 255) / 256, (int64_t)c->num_sms * 8), s);
-        c->launches++;
-        ea.aux = c->aux;
-    } else if (ks->launch_aux) {                                                // per-node flux ingredient (+ zero-fill of du)
-        PhaseScope ps(c, PH_AUX);
-        if (!c->aux || c->aux_doubles < (size_t)N * 4) {                 // up to 4 values per node
-            int rc = dalloc(c, &c->aux, (size_t)N * 4);
-            if (rc) return rc;
-            c->aux_doubles = (size_t)N * 4;
-        }
-        AuxArgs aa;
-        aa.u = u; aa.qe = c->qe; aa.aux = c->aux; aa.zero = atomics ? du : nullptr; aa.npoin = N; aa.phys = c->phys;
-        ks->launch_aux(aa, (int)std::min<int64_t>((N + 255) / 256, (int64_t)c->num_sms * 8), s);
-        c->launches++;
         ea.aux = c->aux;
     } else if (atomics) {
         PhaseScope ps(c, PH_DSS);
         CK(cudaMemsetAsync(du, 0, (size_t)N * q * 8, s));
     }
-    ea.glist = nullptr; ea.gctr = nullptr; ea.nlist = 0; ea.reserve_sms = 0;
+    ea.glist = nullptr; ea.gctr = nullptr; ea.nlist = 0; ea.reserve_sms = 0; ea.exit_ctr = nullptr; ea.exit_budget = 0;
     const bool split = atomics && c->have_halo && c->split_ready && c->n_iface > 0 && ks->has_dyn && E > 0;
     if (split) {
         // interface groups first; their sums are final once that launch ends, so the exchange (second stream, high
         // priority) runs beside the launch over the interior groups, which leaves overlap_sms SMs to it
         const int per_sm = std::max(1, ks->max_blocks_per_sm());
         const int cap = c->num_sms * per_sm;
-        CK(cudaMemsetAsync(c->d_gctr, 0, 2 * sizeof(int), s));
+        CK(cudaMemsetAsync(c->d_gctr, 0, 4 * sizeof(int), s));
         {
             PhaseScope ps(c, PH_ELEM);
             ea.glist = c->d_glist; ea.nlist = c->n_iface; ea.gctr = c->d_gctr; ea.reserve_sms = 0;
@@ -991,6 +1029,8 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
             CK(cudaEventRecord(c->ev_fork, s));
             ea.glist = c->d_glist + c->n_iface; ea.nlist = c->n_inner; ea.gctr = c->d_gctr + 1;
             ea.reserve_sms = std::min(c->overlap_sms, c->num_sms / 2);
+            // the launch carries reserve_sms * per_sm surplus CTAs; only that many may leave a reserved SM unworked
+            ea.exit_ctr = c->d_gctr + 2; ea.exit_budget = ea.reserve_sms * per_sm;
             ks->launch_elem(ea, (int)std::min<int64_t>((int64_t)c->n_inner + (int64_t)ea.reserve_sms * per_sm, cap), s);
             c->launches += 2;
         }
@@ -1002,11 +1042,7 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
             PhaseScope ps(c, PH_HALO);                                   // what is left exposed after the interior launch
             CK(cudaStreamWaitEvent(s, c->ev_join, 0));
         }
-        if (upd.kind == 1) {
-            PhaseScope ps(c, PH_UPDATE);
-            k_lsrk_update<<<nblk(N * q, 256), 256, 0, s>>>(u, c->tmp, du, N * q, upd.A, upd.B, upd.dt, upd.first);
-            c->launches++;
-        }
+        if (upd.kind == 1) stage_update();
         CK(cudaGetLastError());
         return JX_OK;
     }
@@ -1053,11 +1089,7 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
             c->launches++;
         }
     }
-    if (upd.kind == 1) {
-        PhaseScope ps(c, PH_UPDATE);
-        k_lsrk_update<<<nblk(N * q, 256), 256, 0, s>>>(u, c->tmp, du, N * q, upd.A, upd.B, upd.dt, upd.first);
-        c->launches++;
-    }
+    if (upd.kind == 1) stage_update();
     CK(cudaGetLastError());
     return JX_OK;
 }
@@ -1096,7 +1128,10 @@ extern "C" int jx_rhs(jx_ctx *c, double t, const double *u_host, double *du_host
     cudaSetDevice(c->device);
     const size_t bytes = (size_t)c->npoin * c->neqs * 8;
     CK(cudaEventRecord(c->ev0, c->stream));
-    if (u_host) CK(cudaMemcpyAsync(c->u, u_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (u_host) {
+        c->aux_fresh = false;
+        CK(cudaMemcpyAsync(c->u, u_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    }
     StageUpdate upd;
     int rc = rhs_core(c, c->u, c->du, upd);
     if (rc) return rc;

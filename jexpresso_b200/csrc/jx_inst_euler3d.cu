@@ -14,18 +14,15 @@ namespace jx {
     JX_TSET(NGL, ZW, PW, VAR, false, false), JX_TSET(NGL, ZW, PW, VAR, false, true), JX_TSET(NGL, ZW, PW, VAR, true, false), \
     JX_TSET(NGL, ZW, PW, VAR, true, true)
 
-#define JX_T2SET(NGL, VAR, PERT, POW) make_team2_set<NGL, EulerTheta<3, PERT, POW>, (VAR) == 11>(JX_EQ_EULER_THETA, PERT, POW, VAR)
-
 #define JX_TVSET(PERT, POW) make_team_visc_set<5, EulerTheta<3, PERT, POW>, 2, 2>(JX_EQ_EULER_THETA, PERT, POW, 9)
 #define JX_TRISET(PERT, POW) make_tri_set<8, EulerTheta<3, PERT, POW>>(JX_EQ_EULER_THETA, PERT, POW, 12)
 
 const KernelSet *lookup_euler_theta_3d(int ngl, int lpert, int jxpow, int lvisc, int variant) {
-#ifdef JX_MIN_BUILD   // kernel experiments: nop 4, TOTAL, jx_pow only -- generic, team (9) and team2 (10)
+#ifdef JX_MIN_BUILD   // kernel experiments: nop 4, TOTAL, jx_pow only -- generic, team (9), tri (12), viscous team pass
     static const KernelSet table[] = {JX_SET(5, false, true, false), JX_SET(5, false, true, true), JX_TSET(5, 2, 2, 9, false, true),
-                                      JX_T2SET(5, 10, false, true), JX_T2SET(5, 11, false, true), JX_SET(8, false, true, false), JX_TRISET(false, true), JX_TVSET(false, true)};
+                                      JX_SET(8, false, true, false), JX_TRISET(false, true), JX_TVSET(false, true)};
 #else
     static const KernelSet table[] = {JX_ROW(3), JX_ROW(5), JX_ROW(6), JX_ROW(8), JX_TROW(3, 3, 1, 8), JX_TROW(5, 2, 1, 8), JX_TROW(5, 2, 2, 9),
-                                      JX_T2SET(5, 10, false, false), JX_T2SET(5, 10, false, true), JX_T2SET(5, 11, false, false), JX_T2SET(5, 11, false, true),
                                       JX_TRISET(false, false), JX_TRISET(false, true), JX_TRISET(true, false), JX_TRISET(true, true),
                                       JX_TVSET(false, false), JX_TVSET(false, true), JX_TVSET(true, false), JX_TVSET(true, true)};
 #endif

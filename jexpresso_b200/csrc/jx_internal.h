@@ -23,19 +23,18 @@ struct KernelSet {
     void (*launch_bc)(const BcArgs &, cudaStream_t);
     void (*launch_gather)(const GatherArgs &, cudaStream_t);
     void (*launch_aux)(const AuxArgs &, int grid, cudaStream_t);   // nullptr unless the element kernel reads ElemArgs::aux
-    // k_elem_team2: ElemArgs::aux is the node image [npoin][img_rowd] written by launch_image (img_rowd = 0: no image)
-    void (*launch_image)(const ImageArgs &, int grid, cudaStream_t) = nullptr;
-    int img_rowd = 0;
-    int wpos_off = 0, runi_off = 0, runr_off = 0, runl_off = 0, nrun_off = 0, maxrun = 0;   // row-run tables of the pair records
+    // atomics mode: 2N stage update + zero-fill of du + the next evaluation's aux in one sweep (k_stage_fused); set for
+    // the kernels with launch_aux
+    void (*launch_stage)(const StageArgs &, int grid, cudaStream_t) = nullptr;
     // AV viscous term as a pass of its own (k_visc_team) behind an inviscid element kernel: its launcher and the layout of
     // its pair records (nullptr: the element kernel itself carries the viscous pass, or lvisc = 0)
     void (*launch_visc)(const ElemArgs &, const ViscArgs &, int grid, cudaStream_t) = nullptr;
     int (*visc_max_blocks)() = nullptr;
     cudaError_t (*visc_prepare)() = nullptr;
-    int visc_group_bytes = 0, visc_zslot_bytes = 0, visc_zid_off = 0, visc_fid_off = 0;
+    int visc_group_bytes = 0, visc_zid_off = 0, visc_fid_off = 0;
     // rec_layout 5 (element-group records of the team kernels): bytes per group and stream / id offsets
-    int group_bytes = 0, group_nt = 0, zid_off = 0, fid_off = 0, z_off = 0;
- int has_dyn = 0;                                            // launch_elem honours ElemArgs::glist/gctr (interface-first split)
+    int group_bytes = 0, group_nt = 0, zid_off = 0, fid_off = 0, z_off = 0, w_off = 0, wf_off = 0;
+    int has_dyn = 0;                                            // launch_elem honours ElemArgs::glist/gctr (interface-first split)
 };
 
 // each instantiation unit exports one lookup; returns nullptr if it does not hold the combination

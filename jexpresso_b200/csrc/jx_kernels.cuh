@@ -152,6 +152,9 @@ struct BcArgs {
     const double *normal;    // [nhits][3]
     int64_t npoin;
     int nb;
+    double *aux = nullptr;   // non-null: the per-node flux ingredient of the projected nodes is re-evaluated here (the fused
+                             // stage update k_stage_fused produced aux from the unprojected state)
+    Phys phys;
 };
 
 template <class EQ>
@@ -175,6 +178,14 @@ static __global__ void k_bc_dirichlet(BcArgs a) {
     }
 #pragma unroll
     for (int e = 0; e < NEQ; ++e) a.u[(size_t)e * a.npoin + ip] = q[e];
+    if constexpr (EQ::HAS_AUX) {
+        if (a.aux) {
+            double ax[EQ::NAUX > 0 ? EQ::NAUX : 1];
+            EQ::aux(a.phys, q, qe, ax);
+#pragma unroll
+            for (int x = 0; x < EQ::NAUX; ++x) a.aux[(size_t)x * a.npoin + ip] = ax[x];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -194,11 +205,16 @@ struct ElemArgs {
     const double *coords;  // [nsd][npoin] (only read by functors with NEEDS_XYZ)
     const double *aux;     // [NAUX][npoin] per-node part of the flux (k_node_aux), kernels with EQ::HAS_AUX only
     const int32_t *elist;  // optional element subset (interface / interior split); nullptr = all
+    const int32_t *eorig;  // team kernels: record position -> element id (the records are laid out in order_elements() order;
+                           // rhs_el keeps the caller's element numbering, which the deterministic gather walks); nullptr = identity
     const int32_t *glist;  // k_elem_team<DYN>: list of element groups this launch processes (interface or interior set)
     int *gctr;             // k_elem_team<DYN>: work counter (zeroed before the launch); CTAs take list positions from it
     int nlist;             // length of glist
     int reserve_sms;       // k_elem_team<DYN>: CTAs landing on SMs with %smid < reserve_sms exit at once (SMs kept free for
                            // the interface exchange running beside the interior launch)
+    int *exit_ctr;         // k_elem_team<DYN>: how many CTAs have left a reserved SM so far (zeroed before the launch)
+    int exit_budget;       // ... and how many may: the surplus CTAs of the launch.  Every CTA beyond it works wherever it lands,
+                           // so the list is always covered, whatever the block scheduler does with the other SMs
     int64_t nelem, npoin;  // nelem = number of elements this launch processes
     int atomics;
     int lsource;
@@ -532,6 +548,54 @@ static __global__ void k_node_aux(const __grid_constant__ AuxArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Atomics mode: the 2N low-storage stage update (tmp = A*tmp + dt*du, u += B*tmp; k_lsrk_update's expressions), the
+// zero-fill of du for the NEXT evaluation's scatter and the next evaluation's per-node equation of state in ONE sweep
+// over the nodes: the next rhs! then starts at the Dirichlet projection (which re-evaluates aux at the nodes it
+// changes) and the element kernel -- k_node_aux and one full pass over du leave the stage.
+// ------------------------------------------------------------------------------------------
+struct StageArgs {
+    double *u, *tmp, *du;
+    const double *qe;
+    double *aux;      // [NAUX][npoin] or nullptr
+    int64_t npoin;
+    double A, B, dt;
+    int first;
+    Phys phys;
+};
+
+template <class EQ>
+static __global__ void __launch_bounds__(256) k_stage_fused(const __grid_constant__ StageArgs a) {
+    constexpr int NEQ = EQ::NEQ;
+    for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < a.npoin; ip += (int64_t)gridDim.x * blockDim.x) {
+        double d[NEQ], tm[NEQ], q[NEQ], qe[NEQ + 1];
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) d[e] = __ldcs(a.du + (size_t)e * a.npoin + ip);
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) tm[e] = a.first ? 0.0 : __ldcs(a.tmp + (size_t)e * a.npoin + ip);
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) q[e] = a.u[(size_t)e * a.npoin + ip];
+#pragma unroll
+        for (int e = 0; e <= NEQ; ++e) qe[e] = (EQ::NEEDS_QE && EQ::HAS_AUX && (e == NEQ || ((EQ::AUX_MASK >> e) & 1u))) ? a.qe[(size_t)e * a.npoin + ip] : 0.0;
+#pragma unroll
+        for (int e = 0; e < NEQ; ++e) {
+            tm[e] = a.first ? a.dt * d[e] : a.A * tm[e] + a.dt * d[e];
+            q[e] = q[e] + a.B * tm[e];
+            __stcs(a.tmp + (size_t)e * a.npoin + ip, tm[e]);
+            a.u[(size_t)e * a.npoin + ip] = q[e];
+            a.du[(size_t)e * a.npoin + ip] = 0.0;
+        }
+        if constexpr (EQ::HAS_AUX) {
+            if (a.aux) {
+                double ax[EQ::NAUX > 0 ? EQ::NAUX : 1];
+                EQ::aux(a.phys, q, qe, ax);
+#pragma unroll
+                for (int x = 0; x < EQ::NAUX; ++x) a.aux[(size_t)x * a.npoin + ip] = ax[x];
+            }
+        }
+    }
+}
+
 // cp.async (LDGSTS) helpers
 __device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -545,46 +609,48 @@ struct GroupRetileArgs {
     const double *omega;
     const double *Minv;       // slot -2
     const int64_t *connijk;   // slot -1
+    const int32_t *epos;      // element -> position in record order (nullptr: identity); see order_elements()
     char *rec;
     int64_t nelem;
-    int ngl, epb, group_bytes, zid_off, fid_off, z_off;
+    int ngl, epb, group_bytes, zid_off, fid_off, z_off, w_off, wf_off;
     int slot;                 // 0..8 metric term, 9 = Je (stored as omega*J), -1 = node ids, -2 = -(omega*J*Minv)
 };
 
-// element-fastest Julia arrays -> element-group records of the team kernels (layout 5); thread = (element, local node),
-// element fastest.  Plane lane = k + n*(X + 3*s) holds xi_X, eta_X of plane k (streams n*j+i and n*n + n*j+i); zeta lane
-// c = i + n*j of slot s holds zeta_{x,y,z}, omega*J, -(omega*J*Minv) at node k; then the zeta-view and flux-view node ids.
+// element-fastest Julia arrays -> element-group records of the team kernels (layout 5, ElemTeamCfg); thread = (element,
+// local node), element fastest.  Element iel lives in group pos/epb, slot pos%epb, pos = epos[iel].
 static __global__ void k_retile_group(GroupRetileArgs a) {
-    const int n = a.ngl, np = n * n * n;
+    const int n = a.ngl, nc = n * n, np = nc * n;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= a.nelem * np) return;
     const int64_t iel = tid % a.nelem;
     const int l = (int)(tid / a.nelem);
-    const int i = l % n, j = (l / n) % n, k = l / (n * n);
-    const int64_t g = iel / a.epb;
-    const int s = (int)(iel % a.epb);
+    const int i = l % n, j = (l / n) % n, k = l / nc;
+    const int64_t pos = a.epos ? a.epos[iel] : iel;
+    const int64_t g = pos / a.epb;
+    const int s = (int)(pos % a.epb);
     char *rec = a.rec + (size_t)g * a.group_bytes;
-    double *met = reinterpret_cast<double *>(rec);
+    const int npl = 3 * n * a.epb, zrow = a.epb * nc, c = i + n * j;
+    double *pl = reinterpret_cast<double *>(rec);
+    double *zs = reinterpret_cast<double *>(rec + a.z_off);
+    double *w = reinterpret_cast<double *>(rec + a.w_off), *wf = reinterpret_cast<double *>(rec + a.wf_off);
     int32_t *zid = reinterpret_cast<int32_t *>(rec + a.zid_off);
     int32_t *fid = reinterpret_cast<int32_t *>(rec + a.fid_off);
     const size_t src = (size_t)iel + (size_t)a.nelem * l;
-    const int nc = n * n, nstrz = 5 * n, c = i + n * j;
-    double *zs = reinterpret_cast<double *>(rec + a.z_off) + (size_t)s * nstrz * 32;
+    const int zpos = k * zrow + s * nc + c;
     if (a.slot == -1) {
         const int32_t ip = (int32_t)(a.connijk[src] - 1);
-        zid[(s * n + k) * 32 + c] = ip;
+        zid[zpos] = ip;
         fid[s * np + l] = ip;
     } else if (a.slot == -2) {
-        const int32_t ip = zid[(s * n + k) * 32 + c];
-        zs[(4 * n + k) * 32 + c] = -(zs[(3 * n + k) * 32 + c] * a.Minv[ip]);
+        wf[zpos] = -(w[zpos] * a.Minv[zid[zpos]]);
     } else if (a.slot < 6) {
         const int X = a.slot % 3, lane = k + n * (X + 3 * s);
-        met[(size_t)((a.slot < 3 ? 0 : nc) + n * j + i) * 32 + lane] = a.src[src];
+        pl[(size_t)((a.slot < 3 ? 0 : nc) + n * j + i) * npl + lane] = a.src[src];
     } else if (a.slot < 9) {
-        zs[((a.slot - 6) * n + k) * 32 + c] = a.src[src];
+        zs[(size_t)(a.slot - 6) * n * zrow + zpos] = a.src[src];
     } else {
         const double wjk = a.omega[j] * a.omega[k];      // rhs.jl:1636-1643
-        zs[(3 * n + k) * 32 + c] = a.omega[i] * wjk * a.src[src];
+        w[zpos] = a.omega[i] * wjk * a.src[src];
     }
 }
 
@@ -633,19 +699,20 @@ struct ElemTeamCfg {
     static constexpr size_t SMEM_BYTES = (size_t)NTILE * GB * 8;
     static constexpr int NQ = EQ::NEQ - (EQ::FLUX_QMASK == ((1u << (EQ::NEQ - 1)) - 1u) ? 1 : 0);
     static constexpr int NCOMP = NQ + EQ::NAUX;
-    static constexpr int NSTRZ = 5 * NGL;
-    static constexpr int Z_OFF = 2 * NC * 32 * 8;
-    static constexpr int ZID_OFF = Z_OFF + EPB * NSTRZ * 32 * 8;
-    static constexpr int FID_OFF = ZID_OFF + EPB * NGL * 32 * 4;
-    // k_elem_team2 extension (built on the host by build_row_runs, jexrhs.cu): the node-image rows of an element are
-    // fetched in ascending node-id order, consecutive ids merged into one bulk copy ("run")
-    static constexpr int MAXRUN = round_up(NP, 4);
-    static constexpr int WPOS_OFF = FID_OFF + round_up(NNODE * 4, 16);          // uint8[NNODE]: row (within its element) of flux-view node n
-    static constexpr int RUNI_OFF = WPOS_OFF + round_up(NNODE, 16);             // int32[EPB][MAXRUN]: first node id of the run
-    static constexpr int RUNR_OFF = RUNI_OFF + EPB * MAXRUN * 4;                // uint8[EPB][MAXRUN]: first row of the run
-    static constexpr int RUNL_OFF = RUNR_OFF + EPB * MAXRUN;                    // uint8[EPB][MAXRUN]: rows in the run
-    static constexpr int NRUN_OFF = RUNL_OFF + EPB * MAXRUN;                    // int32[EPB]
-    static constexpr int GROUP_BYTES = round_up(NRUN_OFF + EPB * 4, 128);
+    // pair records (layout 5), every row packed to the lanes that read it:
+    //   [0, Z_OFF)        2*NC plane rows of NPL doubles: xi_X (rows n), eta_X (rows NC + n) at plane node n, lane k + N*(X + 3*slot)
+    //   [Z_OFF, W_OFF)    3*N zeta rows of ZROW = EPB*NC doubles: zeta_q at node m of the zeta line, row q*N + m, position slot*NC + c
+    //   [W_OFF, WF_OFF)   N rows of ZROW doubles: omega*J          (MODE 0 / 1)
+    //   [WF_OFF, ZID_OFF) N rows of ZROW doubles: -(omega*J*Minv)  (MODE 2); a launch reads ONE of the two weight blocks
+    //   [ZID_OFF, FID_OFF) int32 zeta-view node ids, N rows of ZROW; then int32 flux-view node ids [EPB*NP]
+    static constexpr int ZROW = EPB * NC;
+    static constexpr int Z_OFF = round_up(2 * NC * NPL * 8, 16);
+    static constexpr int W_OFF = Z_OFF + 3 * NGL * ZROW * 8;
+    static constexpr int WBYTES = round_up(NGL * ZROW * 8, 16);
+    static constexpr int WF_OFF = W_OFF + WBYTES;
+    static constexpr int ZID_OFF = WF_OFF + WBYTES;
+    static constexpr int FID_OFF = ZID_OFF + round_up(NGL * ZROW * 4, 16);
+    static constexpr int GROUP_BYTES = round_up(FID_OFF + NNODE * 4, 128);
 };
 
 // DYN = true: the launch walks a LIST of groups (a.glist) handed out through an atomic counter instead of the static
@@ -657,7 +724,7 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
     using C = ElemTeamCfg<NGL, EQ, ZW, PW>;
     constexpr int SPW = C::SPW;
     constexpr int N = NGL, NC = C::NC, NP = C::NP, NEQ = C::NEQ, NT = C::NT, R = C::R, GB = C::GB, EPB = C::EPB;
-    constexpr int NQ = C::NQ, NCOMP = C::NCOMP, NSTRZ = C::NSTRZ;
+    constexpr int NQ = C::NQ, NCOMP = C::NCOMP, ZROW = C::ZROW, NPL = C::NPL;
     static_assert(EQ::SRC_EQ >= -1, "team kernels keep at most one source component");
     static_assert(EQ::HAS_AUX, "the team kernels use the two-stage flux functors");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -670,6 +737,7 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
     // plane role: lane = k + N*(X + 3*slot)
     const int pk = lane % N, pX = (lane / N) % 3, ps = lane / (3 * N);
     const bool pact = lane < C::NPL;
+    const int plane_l = pact ? lane : 0;                  // inactive lanes re-read lane 0's column (rows are packed to NPL doubles)
     const int poff = ps * NP + NC * pk;                   // plane k of element slot ps inside a tile
     // zeta role: lane c = i + N*j
     const bool zact = lane < NC;
@@ -687,7 +755,11 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
     if constexpr (DYN) {
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        if ((int)smid < a.reserve_sms) return;
+        if ((int)smid < a.reserve_sms) {
+            if (t == 0) s_grp[3] = atomicAdd(a.exit_ctr, 1) < a.exit_budget ? 1 : 0;
+            __syncthreads();
+            if (s_grp[3]) return;
+        }
         if (t == 0) {
             const int p0 = atomicAdd(a.gctr, 1), p1 = atomicAdd(a.gctr, 1);
             s_grp[0] = p0 < a.nlist ? a.glist[p0] : (int)ngroups;
@@ -753,9 +825,13 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
 #pragma unroll
             for (int r = 0; r < R; ++r) fid[r] = r * NT + t < C::NNODE ? __ldcs(fi + r * NT + t) : 0;
 #if JX_TEAM_L2PF
+            // everything this launch reads of the record except the flux-view ids (loaded above): the plane and zeta rows,
+            // ONE of the two weight blocks, the zeta-view ids -- two contiguous ranges
             constexpr int CH = 1024;
-            for (int off = t * CH; off < C::FID_OFF; off += NT * CH)
-                prefetch_l2_bulk(a.rec + (size_t)gn * C::GROUP_BYTES + off, (C::FID_OFF - off) < CH ? (C::FID_OFF - off) : CH);
+            constexpr int A_END = fold ? C::W_OFF : C::WF_OFF, B_BEG = fold ? C::WF_OFF : C::ZID_OFF;
+            const char *rn = a.rec + (size_t)gn * C::GROUP_BYTES;
+            for (int off = t * CH; off < A_END; off += NT * CH) prefetch_l2_bulk(rn + off, (A_END - off) < CH ? (A_END - off) : CH);
+            for (int off = B_BEG + t * CH; off < C::FID_OFF; off += NT * CH) prefetch_l2_bulk(rn + off, (C::FID_OFF - off) < CH ? (C::FID_OFF - off) : CH);
 #endif
         }
     };
@@ -797,7 +873,7 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
             const double *pl = reinterpret_cast<const double *>(a.rec + (size_t)g * C::GROUP_BYTES);
             double mxi[NN], met[NN];             // xi_X, eta_X at this warp's nodes of plane k (lane-major streams)
 #pragma unroll
-            for (int n = 0; n < NN; ++n) { mxi[n] = __ldcs(pl + (LO + n) * 32 + lane); met[n] = __ldcs(pl + (NC + LO + n) * 32 + lane); }
+            for (int n = 0; n < NN; ++n) { mxi[n] = __ldcs(pl + (LO + n) * NPL + plane_l); met[n] = __ldcs(pl + (NC + LO + n) * NPL + plane_l); }
             flux_phase(cnt);
             prefetch_next(next_of(g), fidn);
             block_sync();
@@ -853,20 +929,21 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
             const int cnt = (int)(a.nelem - e0 < EPB ? a.nelem - e0 : EPB);
             const char *rec = a.rec + (size_t)g * C::GROUP_BYTES;
             const double *zs = reinterpret_cast<const double *>(rec + C::Z_OFF);
+            const double *ws = reinterpret_cast<const double *>(rec + (fold ? C::WF_OFF : C::W_OFF));
             const int32_t *zid = reinterpret_cast<const int32_t *>(rec + C::ZID_OFF);
             double mz[SPW][3][N], wj[SPW][N];
             int ip[SPW][N];
 #pragma unroll
             for (int sl = 0; sl < SPW; ++sl) {
-                const int s = zw * SPW + sl;
+                const int zp = (zw * SPW + sl) * NC + c;
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
 #pragma unroll
-                    for (int m = 0; m < N; ++m) mz[sl][q][m] = __ldcs(zs + (s * NSTRZ + q * N + m) * 32 + lane);
+                    for (int m = 0; m < N; ++m) mz[sl][q][m] = __ldcs(zs + (q * N + m) * ZROW + zp);
 #pragma unroll
                 for (int m = 0; m < N; ++m) {
-                    wj[sl][m] = __ldcs(zs + (s * NSTRZ + (fold ? 4 : 3) * N + m) * 32 + lane);
-                    ip[sl][m] = __ldcs(zid + (s * N + m) * 32 + lane);
+                    wj[sl][m] = __ldcs(ws + m * ZROW + zp);
+                    ip[sl][m] = __ldcs(zid + m * ZROW + zp);
                 }
             }
             flux_phase(cnt);
@@ -910,7 +987,11 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
                                     dH[o] = fma(JX_D(m, o), h[m], dH[o]);
                                 }
                             double *due = a.du + (size_t)e * a.npoin;
-                            double *rhe = MODE == 0 ? a.rhs_el + ((size_t)(e0 + s) * NEQ + e) * NP + c : nullptr;
+                            double *rhe = nullptr;
+                            if constexpr (MODE == 0) {
+                                const int64_t eo = a.eorig ? (int64_t)__ldg(a.eorig + e0 + s) : e0 + s;
+                                rhe = a.rhs_el + ((size_t)eo * NEQ + e) * NP + c;
+                            }
 #pragma unroll
                             for (int k = 0; k < N; ++k) {
                                 const double dFdx = b[0][k] + dF[k] * mz[sl][0][k];
@@ -1185,6 +1266,5 @@ static __global__ void k_add_sel(double *a, int64_t npoin, int m, const int64_t 
 
 }  // namespace jx
 
-#include "jx_team2.cuh"
 #include "jx_tri.cuh"
 #include "jx_visc.cuh"

@@ -40,6 +40,13 @@ void launch_aux_t(const AuxArgs &a, int grid, cudaStream_t s) {
     k_node_aux<EQ><<<grid, 256, 0, s>>>(a);
 }
 
+template <class EQ>
+void launch_stage_t(const StageArgs &a, int grid, cudaStream_t s) {
+    if (a.npoin <= 0) return;
+    (void)grid;   // one node per thread: 1.07 ms at 25 M nodes against 1.5-1.7 ms for a persistent grid (scripts/micro/stage_bench.cu)
+    k_stage_fused<EQ><<<(unsigned)((a.npoin + 255) / 256), 256, 0, s>>>(a);
+}
+
 template <int NEQ>
 void launch_gather_t(const GatherArgs &a, cudaStream_t s) {
     if (a.npoin <= 0) return;
@@ -109,65 +116,9 @@ KernelSet make_team_set(int eq_id, int lpert, int jxpow, int variant) {
     ks.launch_bc = &launch_bc_t<EQ>;
     ks.launch_gather = &launch_gather_t<EQ::NEQ>;
     ks.launch_aux = &launch_aux_t<EQ>;
+    ks.launch_stage = &launch_stage_t<EQ>;
     ks.group_bytes = C::GROUP_BYTES; ks.group_nt = 32; ks.zid_off = C::ZID_OFF; ks.fid_off = C::FID_OFF; ks.z_off = C::Z_OFF;
-    ks.has_dyn = 1;
-    return ks;
-}
-
-template <class EQ>
-void launch_image_t(const ImageArgs &a, int grid, cudaStream_t s) {
-    if (a.npoin <= 0) return;
-    k_node_image<EQ><<<grid, 256, 0, s>>>(a);
-}
-
-// variant 10: k_elem_team2 (node image + TMA row gathers, ring of equation slots, producer/consumer barriers)
-template <int NGL, class EQ, bool WT>
-struct Team2Kernel {
-    using C = ElemTeam2Cfg<NGL, EQ, WT>;
-    static cudaError_t prepare() {
-        cudaError_t e = cudaFuncSetAttribute(k_elem_team2<NGL, EQ, 0, false, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_team2<NGL, EQ, 1, false, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_team2<NGL, EQ, 2, false, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_elem_team2<NGL, EQ, 2, true, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-        return e;
-    }
-    static int max_blocks() {
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_elem_team2<NGL, EQ, 2, false, WT>, C::NT, C::SMEM_BYTES);
-        return nb;
-    }
-    static void launch(const ElemArgs &a, int grid, cudaStream_t s) {
-        if (a.gctr != nullptr) {
-            if (a.atomics && a.Minv != nullptr) k_elem_team2<NGL, EQ, 2, true, WT><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
-        } else if (!a.atomics) k_elem_team2<NGL, EQ, 0, false, WT><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
-        else if (a.Minv == nullptr) k_elem_team2<NGL, EQ, 1, false, WT><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
-        else k_elem_team2<NGL, EQ, 2, false, WT><<<grid, C::NT, C::SMEM_BYTES, s>>>(a);
-    }
-};
-
-template <int NGL, class EQ, bool WT>
-KernelSet make_team2_set(int eq_id, int lpert, int jxpow, int variant) {
-    using K = Team2Kernel<NGL, EQ, WT>;
-    using C = typename K::C;
-    using L = typename C::L;
-    KernelSet ks;
-    ks.nsd = 3; ks.ngl = NGL; ks.eq_id = eq_id; ks.lpert = lpert; ks.jxpow = jxpow; ks.lvisc = 0; ks.variant = variant;
-    ks.neq = EQ::NEQ;
-    ks.elems_per_block = C::EPB;
-    ks.rec_layout = 6;                 // layout 5 + row-run tables (build_row_runs)
-    ks.nthreads = C::NT;
-    ks.smem_bytes = C::SMEM_BYTES;
-    ks.prepare = &K::prepare;
-    ks.max_blocks_per_sm = &K::max_blocks;
-    ks.launch_elem = &K::launch;
-    ks.launch_bc = &launch_bc_t<EQ>;
-    ks.launch_gather = &launch_gather_t<EQ::NEQ>;
-    ks.launch_aux = nullptr;
-    ks.launch_image = &launch_image_t<EQ>;
-    ks.img_rowd = C::ROWD;
-    ks.group_bytes = L::GROUP_BYTES; ks.group_nt = 32; ks.zid_off = L::ZID_OFF; ks.fid_off = L::FID_OFF; ks.z_off = L::Z_OFF;
-    ks.wpos_off = L::WPOS_OFF; ks.runi_off = L::RUNI_OFF; ks.runr_off = L::RUNR_OFF; ks.runl_off = L::RUNL_OFF; ks.nrun_off = L::NRUN_OFF;
-    ks.maxrun = L::MAXRUN;
+    ks.w_off = C::W_OFF; ks.wf_off = C::WF_OFF;
     ks.has_dyn = 1;
     return ks;
 }
@@ -211,6 +162,7 @@ KernelSet make_tri_set(int eq_id, int lpert, int jxpow, int variant) {
     ks.launch_bc = &launch_bc_t<EQ>;
     ks.launch_gather = &launch_gather_t<EQ::NEQ>;
     ks.launch_aux = &launch_aux_t<EQ>;
+    ks.launch_stage = &launch_stage_t<EQ>;
     ks.group_bytes = C::REC_BYTES; ks.zid_off = C::ZID_OFF; ks.fid_off = C::FID_OFF;
     return ks;
 }
@@ -244,7 +196,7 @@ KernelSet make_team_visc_set(int eq_id, int lpert, int jxpow, int variant) {
     ks.launch_visc = &V::launch;
     ks.visc_max_blocks = &V::max_blocks;
     ks.visc_prepare = &V::prepare;
-    ks.visc_group_bytes = V::C::GROUP_BYTES; ks.visc_zslot_bytes = V::C::ZSLOT_BYTES; ks.visc_zid_off = V::C::ZID_OFF;
+    ks.visc_group_bytes = V::C::GROUP_BYTES; ks.visc_zid_off = V::C::ZID_OFF;
     ks.visc_fid_off = V::C::FID_OFF;
     return ks;
 }

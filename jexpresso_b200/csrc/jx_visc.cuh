@@ -35,8 +35,10 @@ struct ViscTeamCfg {
     static constexpr int NT = 96, NNODE = EPB * NP, R = (NNODE + NT - 1) / NT;
     static constexpr int GB = (EPB * NP + 12) / 16 * 16 + 3;     // as the team kernel: conflict-free plane and line accesses
     static constexpr int NMET = 11;
-    static constexpr int ZSLOT_BYTES = NMET * NGL * 32 * 8;
-    static constexpr int ZID_OFF = EPB * ZSLOT_BYTES, FID_OFF = ZID_OFF + EPB * NGL * 32 * 4;
+    // viscous pair records: NMET*N rows of ZROW = EPB*NC doubles (row m*N + k: metric m at node k of the zeta line, position
+    // slot*NC + c), then int32 zeta-view node ids (N rows of ZROW) and flux-view node ids [EPB*NP]; rows packed to their lanes
+    static constexpr int ZROW = EPB * NC;
+    static constexpr int ZID_OFF = round_up(NMET * NGL * ZROW * 8, 16), FID_OFF = ZID_OFF + round_up(NGL * ZROW * 4, 16);
     static constexpr int GROUP_BYTES = round_up(FID_OFF + NNODE * 4, 128);
     static constexpr int NTILE = 4 * NEQ;                        // U, D_xi/G_xi/O, D_eta/G_eta, A_zeta per equation
     static constexpr size_t SMEM_BYTES = (size_t)NTILE * GB * 8;
@@ -48,9 +50,10 @@ struct ViscRetileArgs {
     const double *omega;
     const double *Minv;       // slot -2
     const int64_t *connijk;   // slot -1
+    const int32_t *epos;      // element -> position in record order (nullptr: identity)
     char *rec;
     int64_t nelem;
-    int ngl, epb, group_bytes, zslot_bytes, zid_off, fid_off;
+    int ngl, epb, group_bytes, zid_off, fid_off;
     int slot;                 // 0..8 metric term, 9 = Je (stored as omega*J), -1 = node ids, -2 = Minv
 };
 
@@ -61,25 +64,26 @@ static __global__ void k_retile_visc(ViscRetileArgs a) {
     const int64_t iel = tid % a.nelem;
     const int l = (int)(tid / a.nelem);
     const int i = l % n, j = (l / n) % n, k = l / nc;
-    const int64_t g = iel / a.epb;
-    const int s = (int)(iel % a.epb);
+    const int64_t pos = a.epos ? a.epos[iel] : iel;
+    const int64_t g = pos / a.epb;
+    const int s = (int)(pos % a.epb);
     char *rec = a.rec + (size_t)g * a.group_bytes;
-    double *zs = reinterpret_cast<double *>(rec + (size_t)s * a.zslot_bytes);
+    double *zs = reinterpret_cast<double *>(rec);
     int32_t *zid = reinterpret_cast<int32_t *>(rec + a.zid_off);
     int32_t *fid = reinterpret_cast<int32_t *>(rec + a.fid_off);
     const size_t src = (size_t)iel + (size_t)a.nelem * l;
-    const int c = i + n * j;
+    const int zrow = a.epb * nc, zpos = k * zrow + s * nc + i + n * j;
     if (a.slot == -1) {
         const int32_t ip = (int32_t)(a.connijk[src] - 1);
-        zid[(s * n + k) * 32 + c] = ip;
+        zid[zpos] = ip;
         fid[s * np + l] = ip;
     } else if (a.slot == -2) {
-        zs[(size_t)(10 * n + k) * 32 + c] = a.Minv[zid[(s * n + k) * 32 + c]];
+        zs[(size_t)10 * n * zrow + zpos] = a.Minv[zid[zpos]];
     } else if (a.slot < 9) {
-        zs[(size_t)(a.slot * n + k) * 32 + c] = a.src[src];
+        zs[(size_t)a.slot * n * zrow + zpos] = a.src[src];
     } else {
         const double wjk = a.omega[j] * a.omega[k];      // the weight every record layout stores: omega_i*(omega_j*omega_k)*Je
-        zs[(size_t)(9 * n + k) * 32 + c] = a.omega[i] * wjk * a.src[src];
+        zs[(size_t)9 * n * zrow + zpos] = a.omega[i] * wjk * a.src[src];
     }
 }
 
@@ -146,16 +150,16 @@ k_visc_team(const __grid_constant__ ElemArgs a, const __grid_constant__ ViscArgs
         double M[10][N], minv[N];
         int ip[N];
         if (owner) {
-            const double *zs = reinterpret_cast<const double *>(rec + (size_t)warp * C::ZSLOT_BYTES);
-            const int32_t *zid = reinterpret_cast<const int32_t *>(rec + C::ZID_OFF);
+            const double *zs = reinterpret_cast<const double *>(rec) + warp * NC + c;
+            const int32_t *zid = reinterpret_cast<const int32_t *>(rec + C::ZID_OFF) + warp * NC + c;
 #pragma unroll
             for (int m = 0; m < 10; ++m)
 #pragma unroll
-                for (int k = 0; k < N; ++k) M[m][k] = __ldcs(zs + (m * N + k) * 32 + lane);
+                for (int k = 0; k < N; ++k) M[m][k] = __ldcs(zs + (m * N + k) * C::ZROW);
 #pragma unroll
             for (int k = 0; k < N; ++k) {
-                minv[k] = MODE == 2 ? __ldcs(zs + (10 * N + k) * 32 + lane) : 1.0;
-                ip[k] = __ldcs(zid + (warp * N + k) * 32 + lane);
+                minv[k] = MODE == 2 ? __ldcs(zs + (10 * N + k) * C::ZROW) : 1.0;
+                ip[k] = __ldcs(zid + k * C::ZROW);
             }
         }
         // ---- primitives at every node of the pair, node-parallel ----
@@ -318,7 +322,11 @@ k_visc_team(const __grid_constant__ ElemArgs a, const __grid_constant__ ViscArgs
                         } else {
                             const double *Ox = Dx(v) + lo, *Azp = Az(v) + lo;
                             double *due = a.du + (size_t)e * a.npoin;
-                            double *oel = MODE == 0 ? va.out_el + ((size_t)(g * EPB + warp) * NEQ + e) * NP + c : nullptr;
+                            double *oel = nullptr;
+                            if constexpr (MODE == 0) {
+                                const int64_t eo = a.eorig ? (int64_t)__ldg(a.eorig + g * EPB + warp) : g * EPB + warp;
+                                oel = va.out_el + ((size_t)eo * NEQ + e) * NP + c;
+                            }
 #pragma unroll
                             for (int k = 0; k < N; ++k) {
                                 const double outv = Ox[NC * k] + Azp[NC * k];      // (a_xi + a_eta) + a_zeta

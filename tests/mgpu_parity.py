@@ -29,15 +29,19 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
     cases = (((True, True, False), True, 0, 0, (6, 4, 3), 0), ((False, False, False), False, 0, 9, (6, 4, 3), 0),
-             ((True, True, False), False, 1, 9, (6, 4, 3), 0), ((False, False, False), False, 1, 9, (12, 12, 3), 2))
+             ((True, True, False), False, 1, 9, (6, 4, 3), 0), ((False, False, False), False, 1, 9, (12, 12, 3), 2),
+             # BASELINE configs[3] at its stated size (64 x 64 x 24 elements, periodic x,y, AV): opt-in, JX_MGPU_CASES=4,5
+             ((True, True, False), True, 0, 0, (64, 64, 24), 0), ((True, True, False), True, 1, 0, (64, 64, 24), 4))
     pick = os.environ.get("JX_MGPU_CASES")
-    pick = {int(x) for x in pick.split(",")} if pick else set(range(len(cases)))
+    pick = {int(x) for x in pick.split(",")} if pick else set(range(4))
     for ci, (periodic, lvisc, dss, variant, nel, overlap) in enumerate(cases):
         if ci not in pick:
             continue
         box = [capi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        spec = box3d(nel, 4, warp=0.05, periodic=periodic)
+        big = nel[0] * nel[1] * nel[2] > 10000
+        nsteps = 1 if big else 3
+        spec = box3d(nel, 4, warp=0.05, periodic=periodic, L=(10000.0, 10000.0, 3750.0)) if big else box3d(nel, 4, warp=0.05, periodic=periodic)
         sems, qns, qes, us = euler_case(spec, world, lpert=False)
         probs = [ref.RefProblem(s, qe, eq_id=0, lpert=False, lsource=True, lvisc=lvisc, visc_coeff=MU3, phys=PHYS, pow_mode=1)
                  for s, qe in zip(sems, qes)]
@@ -57,11 +61,11 @@ def main():
             du = np.empty_like(u)
             jrhs.rhs_bang(du, u, p, 0.0)
             ug = us[rank].copy()
-            jrhs.time_loop_bang(inputs, p, ug, 3)
+            jrhs.time_loop_bang(inputs, p, ug, nsteps)
         finally:
             p.close()
         us2 = [x.copy() for x in us]
-        ref.time_loop(run, us2, 0.0, inputs["dt"], 3, scheme="CK2N54")
+        ref.time_loop(run, us2, 0.0, inputs["dt"], nsteps, scheme="CK2N54")
         pn, l2 = rel_err_per_node(du, duo[rank])
         pn2, l22 = rel_err_per_node(ug, us2[rank])
         exact = bool(np.array_equal(du, duo[rank]) and np.array_equal(ug, us2[rank]))
@@ -69,8 +73,8 @@ def main():
         if overlap:
             good = good and split[0] > 0 and split[1] > 0
         ok &= good
-        print(f"[rank {rank}/{world}] periodic={periodic} visc={lvisc} dss={dss} kernel={variant} overlap={overlap} split={split}: rhs pn={pn:.2e} l2={l2:.2e} "
-              f"3 steps pn={pn2:.2e} l2={l22:.2e} bit_exact={exact} -> {'OK' if good else 'FAIL'}", flush=True)
+        print(f"[rank {rank}/{world}] nel={nel} periodic={periodic} visc={lvisc} dss={dss} kernel={variant} overlap={overlap} split={split}: rhs pn={pn:.2e} l2={l2:.2e} "
+              f"{nsteps} steps pn={pn2:.2e} l2={l22:.2e} bit_exact={exact} -> {'OK' if good else 'FAIL'}", flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     dist.destroy_process_group()

@@ -253,7 +253,7 @@ def test_device_built_metrics_bit_exact(nsd, nop):
         assert np.array_equal(du2, dus[0]), rel_err_per_node(du2, dus[0])
 
 
-# ---- warp-team element kernels (JX_OPT_ELEM_KERNEL 8 / 9: k_elem_team; 10 / 11: k_elem_team2) ----------------
+# ---- warp-team element kernels (JX_OPT_ELEM_KERNEL 8 / 9: k_elem_team) ----------------
 @pytest.mark.parametrize("variant", [8, 9])
 @pytest.mark.parametrize("nop", [2, 4])
 @pytest.mark.parametrize("lpert", [False, True])
@@ -271,13 +271,11 @@ def test_team_kernel_bit_exact(variant, nop, lpert):
     assert np.array_equal(du, dus[0]), rel_err_per_node(du, dus[0])
 
 
-@pytest.mark.parametrize("variant", [8, 9, 11])
+@pytest.mark.parametrize("variant", [8, 9])
 @pytest.mark.parametrize("lpert", [False, True])
 def test_team_kernel_atomics(variant, lpert):
     """The bench configuration: team kernel + atomics DSS with M^-1 folded in; <= 1e-12 per node, <= 1e-10 relative L2
     (north-star bars; the slack covers the unordered DSS sum)."""
-    if variant == 11 and lpert:
-        pytest.skip("k_elem_team2 is instantiated for TOTAL")
     spec = box3d((7, 5, 3), 4, warp=0.05)      # 105 elements: ragged last pair
     sems, qns, qes, us = euler_case(spec, 1, lpert=lpert)
     dus, ub, _ = _oracle_rhs(sems, qes, us, lpert, False, pow_mode=1)
@@ -336,31 +334,32 @@ def test_tri_kernel_nop7_bit_exact(lpert):
         assert pn <= 1e-12 and l2 <= 1e-10, (e, pn, l2)
 
 
-@pytest.mark.parametrize("variant", [10, 11])
-@pytest.mark.parametrize("nel", [(5, 3, 3), (13, 11, 9), (21, 19, 21)])
-def test_team2_kernel_bit_exact(nel, variant):
-    """k_elem_team2 (variants 10 / 11: node image + TMA row gathers, ring of equation slots, producer/consumer barriers;
-    10 lands the rows in dead ring slots, 11 in a dedicated tile):
-    same order of every sum as the reference, so bit-exact against the oracle.  Odd element counts leave a ragged last
-    pair; 8379 elements give every CTA of the persistent grid (148 SMs x 4) seven pairs, so the slot ring goes once
-    round and the two-buffer hand-shakes wrap many times."""
+@pytest.mark.parametrize("nel", [(13, 11, 9), (21, 19, 21)])
+@pytest.mark.parametrize("order", ["1", "0"])
+def test_team_kernel_record_order(nel, order, monkeypatch):
+    """The pair records of the team kernels are laid out along a Morton curve through the element centres (order_elements,
+    jexrhs.cu; JX_ELEM_ORDER=0 keeps the caller's order).  Pure data placement: with either order the deterministic path is
+    bit-identical to the oracle (rhs_el keeps the caller's element numbering, the gather its element-ascending sums), with
+    and without the AV viscous pass, and the atomics path stays inside its bars.  8379 elements give every CTA of the
+    persistent grid (148 SMs x 4) seven pairs."""
+    monkeypatch.setenv("JX_ELEM_ORDER", order)
     spec = box3d(nel, 4, warp=0.05)
     sems, qns, qes, us = euler_case(spec, 1, lpert=False)
-    dus, ub, _ = _oracle_rhs(sems, qes, us, False, False, pow_mode=1)
-    du, u = _gpu_rhs(sems, qes, us, False, False, pow_mode=1, dss_mode=0, elem_kernel=variant)
-    assert np.array_equal(u, ub[0])
-    assert np.array_equal(du, dus[0]), rel_err_per_node(du, dus[0])
-    # the bench configuration: RED.ADD scatter with M^-1 folded into the weight
-    du, u = _gpu_rhs(sems, qes, us, False, False, pow_mode=1, dss_mode=1, elem_kernel=variant)
-    N = sems[0].mesh.npoin
-    for e in range(5):
-        pn, l2 = rel_err_per_node(du[e * N:(e + 1) * N], dus[0][e * N:(e + 1) * N])
-        assert pn <= 1e-12 and l2 <= 1e-10, (e, pn, l2)
+    for lvisc in (False, True):
+        dus, ub, _ = _oracle_rhs(sems, qes, us, False, lvisc, pow_mode=1)
+        du, u = _gpu_rhs(sems, qes, us, False, lvisc, pow_mode=1, dss_mode=0, elem_kernel=9)
+        assert np.array_equal(u, ub[0])
+        assert np.array_equal(du, dus[0]), (lvisc, rel_err_per_node(du, dus[0]))
+        du, u = _gpu_rhs(sems, qes, us, False, lvisc, pow_mode=1, dss_mode=1, elem_kernel=9)
+        N = sems[0].mesh.npoin
+        for e in range(5):
+            pn, l2 = rel_err_per_node(du[e * N:(e + 1) * N], dus[0][e * N:(e + 1) * N])
+            assert pn <= 1e-12 and l2 <= 1e-10, (lvisc, e, pn, l2)
 
 
 def test_kernel_variant_requires_its_record_layout_before_upload():
-    """k_elem_team2 (variants 10/11) reads pair records extended by the row-run tables (layout 6), and the generic kernel
-    per-element records (layout 0): switching to a kernel of another layout after the upload is refused with JX_ESTATE,
+    """The team kernels read pair records (layout 5), the generic kernel per-element records (layout 0): switching to a
+    kernel of another layout after the upload is refused with JX_ESTATE,
     a variant that is not compiled with JX_EINVAL, and the context keeps working with the kernel it had."""
     from jexpresso_b200 import capi
     spec = box3d((3, 3, 3), 4)
@@ -368,7 +367,7 @@ def test_kernel_variant_requires_its_record_layout_before_upload():
     p = jrhs.params_setup(sems[0], qes[0], _inputs(False, False, 3), pow_mode=1, dss_mode=0, elem_kernel=0)
     try:
         with pytest.raises(capi.JexError) as ei:
-            p.ctx.set_option(capi.JX_OPT_ELEM_KERNEL, 10)
+            p.ctx.set_option(capi.JX_OPT_ELEM_KERNEL, 9)
         assert ei.value.code == capi.JX_ESTATE
         with pytest.raises(capi.JexError) as ei:
             p.ctx.set_option(capi.JX_OPT_ELEM_KERNEL, 3)        # a round-1 pencil variant: no longer compiled

@@ -75,3 +75,57 @@ def test_full_size_cross_kernel_consistency():
 
 def capi_elem_auto():
     return 0        # JX_ELEM_AUTO: the warp-team kernel for 3D inviscid nop 4
+
+
+def _oracle_and_gpu(spec, mu, nsteps, dt):
+    """One rhs! and ``nsteps`` CK2N54 steps of the CompEuler theta case on ``spec``: (oracle du, oracle u_end, GPU du, GPU u_end),
+    deterministic DSS on the GPU, so the comparison is bit for bit."""
+    from helpers import PHYS, euler_case
+    from oracle import ref
+    sems, qns, qes, us = euler_case(spec, 1, lpert=False)
+    prob = ref.RefProblem(sems[0], qes[0], eq_id=0, lpert=False, lsource=True, lvisc=True, visc_coeff=mu, phys=PHYS, pow_mode=1)
+    m = sems[0].mesh
+    caches = ref.setup_assembler([m.ip2gip], [m.gip2owner]) if any(spec.periodic) else None
+    run = ref.RefRun([prob], caches)
+    uo, duo = [us[0].copy()], [np.zeros_like(us[0])]
+    run.rhs(duo, uo, 0.0)
+    ue = [us[0].copy()]
+    ref.time_loop(run, ue, 0.0, dt, nsteps, scheme="CK2N54")
+    inputs = {"SOL_VARS_TYPE": "TOTAL", "lsource": True, "lvisc": True, "mu": mu, "dt": dt, "ode_solver": "CarpenterKennedy2N54"}
+    p = jrhs.params_setup(sems[0], qes[0], inputs, pow_mode=1, dss_mode=0)
+    try:
+        u = us[0].copy()
+        du = np.empty_like(u)
+        jrhs.rhs_bang(du, u, p, 0.0)
+        ug = us[0].copy()
+        jrhs.time_loop_bang(inputs, p, ug, nsteps)
+        variant = p.ctx.kernel_variant()
+    finally:
+        p.close()
+    return duo[0], ue[0], du, ug, variant
+
+
+def test_c3_density_current_box_at_stated_size():
+    """BASELINE configs[2] at its stated size: 2D, 128 x 32 elements, nop 5, AV viscous term (the viscous-kernel path,
+    rhs.jl:1973-2056): one rhs! and 20 CK2N54 steps, bit-exact against the oracle."""
+    from helpers import MU2, box2d
+    spec = box2d((128, 32), 5, warp=0.05, lo=(0.0, 0.0), hi=(25600.0, 6400.0))
+    duo, ue, du, ug, variant = _oracle_and_gpu(spec, MU2, 20, 0.02)
+    assert np.isfinite(du).all() and np.isfinite(ug).all()
+    assert np.array_equal(du, duo), rel_err_per_node(du, duo)
+    assert np.array_equal(ug, ue), rel_err_per_node(ug, ue)
+
+
+def test_c4_abl_box_at_stated_size_one_gpu():
+    """BASELINE configs[3] at its stated size on one GPU: 3D, 64 x 64 x 24 elements, nop 4, periodic in x and y (the twins
+    are summed through the assembler's self lists, restructure_for_periodicity.jl:1387-1577 / mpi_communications.jl:99-112),
+    free-slip top and bottom, AV viscous term: one rhs! and one CK2N54 step, bit-exact against the oracle.  (The 2/4/8-rank
+    NCCL runs of the same mesh: tests/mgpu_parity.py cases 4 and 5, profiles/.)"""
+    from helpers import MU3, box3d
+    nel = tuple(int(x) for x in os.environ.get("JX_C4_NEL", "64,64,24").split(","))
+    spec = box3d(nel, 4, warp=0.05, periodic=(True, True, False), L=(10000.0, 10000.0, 3750.0))
+    duo, ue, du, ug, variant = _oracle_and_gpu(spec, MU3, 1, 0.05)
+    assert variant == 9, variant       # the warp-team kernels (inviscid + viscous pass) carry this configuration
+    assert np.isfinite(du).all() and np.isfinite(ug).all()
+    assert np.array_equal(du, duo), rel_err_per_node(du, duo)
+    assert np.array_equal(ug, ue), rel_err_per_node(ug, ue)
