@@ -241,6 +241,8 @@ def workload_name(a):
 def elem_kernel_name(ctx_variant, a):
     if a.visc and ctx_variant == 9:
         return "k_elem_team + k_visc_team (inviscid warp-team kernel followed by the AV viscous warp-team pass)"
+    if a.visc and ctx_variant == 13:
+        return "k_elem_team + k_visc_quad (inviscid warp-team kernel followed by the four-warp AV viscous pass)"
     return {9: "k_elem_team (fused flux + divergence per element pair; variant 9)",
             8: "k_elem_team (variant 8)",
             12: "k_elem_tri (three-role pencil kernel, nop 7)"}.get(
@@ -261,7 +263,7 @@ def main():
     ap.add_argument("--dss-mode", type=int, default=int(os.environ.get("JX_DSS_MODE", "1")))
     ap.add_argument("--pow-mode", type=int, default=int(os.environ.get("JX_POW_MODE", "1")))
     ap.add_argument("--elem-kernel", type=int, default=int(os.environ.get("JX_ELEM_KERNEL", "0")),
-                    help="JX_OPT_ELEM_KERNEL: 0 = JX_ELEM_AUTO (fastest exact-order kernel of the configuration), -1 generic, 8 / 9 / 12 a variant")
+                    help="JX_OPT_ELEM_KERNEL: 0 = JX_ELEM_AUTO (fastest exact-order kernel of the configuration), -1 generic, 8 / 9 / 12 / 13 a variant")
     ap.add_argument("--graph", type=int, default=int(os.environ.get("JX_BENCH_GRAPH", "1")),
                     help="1: the timed regions replay one captured evaluation as a CUDA graph (declared mode); 0: eager enqueue")
     ap.add_argument("--overlap", type=int, default=int(os.environ.get("JX_OVERLAP", "-1")),

@@ -63,7 +63,8 @@ typedef struct jx_ctx jx_ctx;
 #define JX_OPT_ELEM_KERNEL 3   /* element-kernel variant: JX_ELEM_AUTO (default) picks the fastest exact-order kernel that
                                   exists for the configuration (3D inviscid nop 2/4: the warp-team kernel, else the generic
                                   one); JX_ELEM_GENERIC forces the generic thread-per-node kernel; 8 / 9 name the warp-team kernel
-                                  (one / two plane warps), 12 the three-role pencil kernel of nop 7 (opt-in).
+                                  (one / two plane warps; with AV: followed by k_visc_team), 13 = 9 followed by the four-warp viscous pass
+                                  k_visc_quad (the AV default), 12 the three-role pencil kernel of nop 7 (opt-in).
                                   All variants keep the reference's order of every sum: bit-identical results. */
 #define JX_ELEM_AUTO 0
 #define JX_ELEM_GENERIC (-1)

@@ -111,6 +111,7 @@ struct jx_ctx {
     const KernelSet *ks = nullptr;
     int np = 0, nmet = 0, rec_bytes = 0;
     int rec_layout = -1;             // layout the resident element records were built with (-1: none)
+    int visc_layout = 0;             // ... and the viscous pair records (KernelSet::visc_layout)
 
     // options
     int dss_mode = 0, pow_mode = 0, elem_variant = 0;
@@ -120,7 +121,12 @@ struct jx_ctx {
     double *rhs_el = nullptr, *rhs_el_visc = nullptr;
     double *aux = nullptr;           // per-node flux ingredient (k_node_aux)
     size_t aux_doubles = 0;
-    bool aux_fresh = false;          // k_stage_fused left aux = aux(c->u) and c->du zeroed: the next rhs_core(c->u, c->du) skips k_node_aux
+    bool aux_fresh = false;          // k_stage_direct left aux = aux(c->u): the next rhs_core on c->u skips k_node_aux
+    bool acc_ready = false;          // c->tmp holds the low-storage register S' = S/dt pre-scaled by acc_A (direct accumulation)
+    double acc_A = 0.0;
+    int64_t *d_ifn = nullptr;        // unique nodes of the assembler lists (interface / periodic twins), ascending
+    int64_t n_ifn = 0;
+    double *d_ifbase = nullptr;      // their share of S' while the exchange sums the pure contributions
     char *rec = nullptr;
     char *rec_visc = nullptr;        // pair records of the viscous pass (k_visc_team), lvisc only
     int32_t *d_eorig = nullptr;      // team records: position -> element id (order_elements); nullptr = identity
@@ -242,6 +248,7 @@ void free_mesh(jx_ctx *c) {
     for (auto &p : c->ss) dfree(p);
     c->have_mesh = false;
     c->rec_layout = -1;
+    c->visc_layout = 0;
 }
 void free_bcs(jx_ctx *c) {
     dfree(c->bc_node); dfree(c->bc_ptr); dfree(c->bc_normal);
@@ -250,7 +257,8 @@ void free_bcs(jx_ctx *c) {
 void free_halo(jx_ctx *c) {
     free_split(c);
     dfree(c->d_send_i); dfree(c->d_recv_idx); dfree(c->d_recvback_idx); dfree(c->d_sendbuf); dfree(c->d_recvbuf);
-    dfree(c->d_add_sel);
+    dfree(c->d_add_sel); dfree(c->d_ifn); dfree(c->d_ifbase);
+    c->n_ifn = 0;
     c->send_seg.clear(); c->recv_seg.clear(); c->add_rounds.clear();
     c->nsend = c->nrecv = 0;
     c->have_halo = false;
@@ -267,10 +275,11 @@ int select_kernels(jx_ctx *c) {
         // fastest exact-order kernel that exists for this configuration: the warp-team kernels (bit-identical to the
         // generic one), else the generic thread-per-node kernel.  Resident records pin the choice to their layout.
         // 9/8: nop 4/2.  Opt-in only: 12 (k_elem_tri, nop 7: 23.8 GDOF/s against 27.5 for the generic kernel, profiles/r02c)
-        const int order[] = {9, 8, 0};
+        // 13 = 9 + the four-warp viscous pass k_visc_quad (AV decks; 21.6 against 18.7 GDOF/s for k_visc_team, profiles/r02e)
+        const int order[] = {13, 9, 8, 0};
         for (int v : order) {
             ks = lookup(v);
-            if (ks && (!c->have_mesh || ks->rec_layout == c->rec_layout)) break;
+            if (ks && (!c->have_mesh || (ks->rec_layout == c->rec_layout && ks->visc_layout == c->visc_layout))) break;
             ks = nullptr;
         }
     } else {
@@ -280,9 +289,9 @@ int select_kernels(jx_ctx *c) {
         return fail(c, JX_EINVAL, "no kernel for nsd=%d ngl=%d eq=%d lpert=%d pow=%d lvisc=%d variant=%d", c->nsd, c->ngl,
                     c->eq_id, c->lpert, c->pow_mode, c->lvisc, c->elem_variant);
     if (ks->neq != c->neqs) return fail(c, JX_EINVAL, "equation set %d has %d equations, got neqs=%d", c->eq_id, ks->neq, c->neqs);
-    if (c->have_mesh && ks->rec_layout != c->rec_layout)
-        return fail(c, JX_ESTATE, "kernel variant %d reads element-record layout %d, the resident records have layout %d: "
-                    "set JX_OPT_ELEM_KERNEL before jx_upload_mesh", ks->variant, ks->rec_layout, c->rec_layout);
+    if (c->have_mesh && (ks->rec_layout != c->rec_layout || ks->visc_layout != c->visc_layout))
+        return fail(c, JX_ESTATE, "kernel variant %d reads element-record layout %d/%d, the resident records have layout %d/%d: "
+                    "set JX_OPT_ELEM_KERNEL before jx_upload_mesh", ks->variant, ks->rec_layout, ks->visc_layout, c->rec_layout, c->visc_layout);
     CK(ks->prepare());
     if (ks->visc_prepare) CK(ks->visc_prepare());
     c->ks = ks;
@@ -373,7 +382,7 @@ extern "C" int jx_last_error(jx_ctx *c, char *buf, int len) {
 
 extern "C" int jx_set_option(jx_ctx *c, int key, int64_t value) {
     if (!c) return JX_EINVAL;
-    if (key != JX_OPT_CUDA_GRAPH) c->aux_fresh = false;
+    if (key != JX_OPT_CUDA_GRAPH) { c->aux_fresh = false; c->acc_ready = false; }
     const int old_dss = c->dss_mode, old_pow = c->pow_mode, old_var = c->elem_variant;
     switch (key) {
         case JX_OPT_DSS_MODE:
@@ -409,7 +418,7 @@ extern "C" int jx_set_problem(jx_ctx *c, int nsd, int ngl, int neqs, int64_t nel
         return fail(c, JX_EINVAL, "jx_set_problem: bad dimensions");
     if (npoin >= (int64_t)1 << 31) return fail(c, JX_EINVAL, "npoin must be < 2^31 per rank");
     cudaSetDevice(c->device);
-    c->aux_fresh = false;
+    c->aux_fresh = false; c->acc_ready = false;
     free_mesh(c); free_bcs(c); free_halo(c);
     c->nsd = nsd; c->ngl = ngl; c->neqs = neqs; c->nelem = nelem; c->npoin = npoin;
     c->eq_id = equation_id; c->lpert = lpert ? 1 : 0; c->lsource = lsource ? 1 : 0; c->lvisc = lvisc ? 1 : 0;
@@ -601,7 +610,7 @@ int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, co
             vr.ngl = c->ngl; vr.epb = ks->elems_per_block; vr.group_bytes = ks->visc_group_bytes;
             vr.zid_off = ks->visc_zid_off; vr.fid_off = ks->visc_fid_off;
             vr.slot = -1;
-            k_retile_visc<<<nblk(total, 256), 256, 0, c->stream>>>(vr);
+            ks->retile_visc(vr, (unsigned)nblk(total, 256), c->stream);
         }
         for (int m = 0; m < c->nmet; ++m) {
             if (metrics && !metrics[m]) { cleanup(); return fail(c, JX_EINVAL, "metric array %d is null", m); }
@@ -610,7 +619,7 @@ int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, co
             k_retile_group<<<nblk(total, 256), 256, 0, c->stream>>>(ga);
             if (with_visc) {
                 vr.src = d_stage; vr.slot = m;
-                k_retile_visc<<<nblk(total, 256), 256, 0, c->stream>>>(vr);
+                ks->retile_visc(vr, (unsigned)nblk(total, 256), c->stream);
             }
             CKC(cudaStreamSynchronize(c->stream));
         }
@@ -618,7 +627,7 @@ int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, co
         k_retile_group<<<nblk(total, 256), 256, 0, c->stream>>>(ga);
         if (with_visc) {
             vr.slot = -2;
-            k_retile_visc<<<nblk(total, 256), 256, 0, c->stream>>>(vr);
+            ks->retile_visc(vr, (unsigned)nblk(total, 256), c->stream);
         }
         c->launches += (c->nmet + 2) * (with_visc ? 2 : 1);
     } else if (total > 0) {
@@ -658,8 +667,9 @@ int upload_mesh_impl(jx_ctx *c, const int64_t *connijk, const double *coords, co
     cleanup();
 #undef CKC
     c->have_mesh = true;
-    c->aux_fresh = false;
+    c->aux_fresh = false; c->acc_ready = false;
     c->rec_layout = c->ks->rec_layout;
+    c->visc_layout = c->ks->visc_layout;
     return JX_OK;
 }
 
@@ -790,6 +800,17 @@ extern "C" int jx_upload_halo(jx_ctx *c, const int64_t *send_ptr, const int64_t 
     CK(cudaMemcpy(c->d_recv_idx, r0.data(), (size_t)nr * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_recvback_idx, b0.data(), (size_t)ns * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_add_sel, sel.data(), sel.size() * 8, cudaMemcpyHostToDevice));
+    {   // unique nodes of the lists (direct accumulation sets their share of the low-storage register aside, rhs_core)
+        std::vector<int64_t> un;
+        un.reserve(s0.size() + r0.size() + b0.size());
+        un.insert(un.end(), s0.begin(), s0.end()); un.insert(un.end(), r0.begin(), r0.end()); un.insert(un.end(), b0.begin(), b0.end());
+        std::sort(un.begin(), un.end());
+        un.erase(std::unique(un.begin(), un.end()), un.end());
+        c->n_ifn = (int64_t)un.size();
+        if ((rc = dalloc(c, &c->d_ifn, un.size())) || (rc = dalloc(c, &c->d_ifbase, un.size() * c->neqs))) return rc;
+        CK(cudaMemcpy(c->d_ifn, un.data(), un.size() * 8, cudaMemcpyHostToDevice));
+    }
+    c->acc_ready = false;
     c->have_halo = true;
     return JX_OK;
 }
@@ -933,10 +954,14 @@ int ensure_split(jx_ctx *c) {
 }
 
 struct StageUpdate {
-    int kind = 0;          // 0: du = Minv*RHS only; 1: 2N low-storage update of (u, tmp)
-    double A = 0, B = 0, dt = 0;
+    int kind = 0;          // 0: du = Minv*RHS only; 1: 2N low-storage update of (u, tmp) behind it; 2: direct accumulation --
+                           // the element kernels add into the low-storage register itself (k_stage_direct), no du
+    double A = 0, B = 0, dt = 0, Anext = 0;
     int first = 0;
 };
+
+// kind 2 is possible with the unordered scatter on the context's own state when the kernel set has the per-node pre-pass
+bool direct_ok(const jx_ctx *c) { return c->dss_mode == 1 && c->ks && c->ks->launch_aux && c->ks->launch_stage; }
 
 // rhs!(du, u, params, t) on the device (rhs.jl:121-134, 498-711).  `u` is projected in place by
 // the Dirichlet kernel; the mass-scaled result lands in `du`; with upd.kind == 1 the low-storage
@@ -951,9 +976,10 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     const int64_t N = c->npoin, E = c->nelem;
     const int q = c->neqs;
     const bool atomics = c->dss_mode == 1;
-    // the previous stage's fused update already zeroed du and evaluated aux on this state (k_stage_fused)
-    const bool own_state = atomics && u == c->u && du == c->du && ks->launch_aux && ks->launch_stage;
-    const bool fresh = c->aux_fresh && own_state && c->aux;
+    const bool direct = upd.kind == 2;                                   // caller checked direct_ok(c) and passes u == c->u
+    double *acc = direct ? c->tmp : du;                                  // where the scatter lands
+    // the previous stage's sweep (k_stage_direct) already evaluated aux on this state
+    const bool fresh = c->aux_fresh && atomics && u == c->u && ks->launch_aux && c->aux;
     c->aux_fresh = false;
     if (c->nb > 0) {                                                     // rhs.jl:558
         PhaseScope ps(c, PH_BC);
@@ -965,14 +991,16 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     }
     auto stage_update = [&]() {
         PhaseScope ps(c, PH_UPDATE);
-        if (own_state && c->aux) {
+        if (direct) {
             StageArgs sa;
-            sa.u = u; sa.tmp = c->tmp; sa.du = du; sa.qe = c->qe; sa.aux = c->aux; sa.npoin = N;
-            sa.A = upd.A; sa.B = upd.B; sa.dt = upd.dt; sa.first = upd.first; sa.phys = c->phys;
-            ks->launch_stage(sa, (int)std::min<int64_t>((N + 255) / 256, (int64_t)c->num_sms * 8), s);
+            sa.u = u; sa.acc = acc; sa.qe = c->qe; sa.aux = c->aux; sa.npoin = N;
+            sa.Bdt = upd.B * upd.dt; sa.Anext = upd.Anext; sa.phys = c->phys;
+            ks->launch_stage(sa, 0, s);
             c->aux_fresh = true;
+            c->acc_ready = true; c->acc_A = upd.Anext;
         } else {
             k_lsrk_update<<<nblk(N * q, 256), 256, 0, s>>>(u, c->tmp, du, N * q, upd.A, upd.B, upd.dt, upd.first);
+            c->acc_ready = false;
         }
         c->launches++;
     };
@@ -997,23 +1025,47 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     const bool fold_minv = atomics;
     ea.aux = nullptr;
     if (ks->launch_aux) {                                                // per-node flux ingredient (+ zero-fill of du)
+        if (!c->aux || c->aux_doubles < (size_t)N * 4) {                 // up to 4 values per node
+            int rc = dalloc(c, &c->aux, (size_t)N * 4);
+            if (rc) return rc;
+            c->aux_doubles = (size_t)N * 4;
+        }
         if (!fresh) {
             PhaseScope ps(c, PH_AUX);
-            if (!c->aux || c->aux_doubles < (size_t)N * 4) {                 // up to 4 values per node
-                int rc = dalloc(c, &c->aux, (size_t)N * 4);
-                if (rc) return rc;
-                c->aux_doubles = (size_t)N * 4;
-            }
             AuxArgs aa;
-            aa.u = u; aa.qe = c->qe; aa.aux = c->aux; aa.zero = atomics ? du : nullptr; aa.npoin = N; aa.phys = c->phys;
+            aa.u = u; aa.qe = c->qe; aa.aux = c->aux; aa.zero = (atomics && !direct) ? du : nullptr; aa.npoin = N; aa.phys = c->phys;
             ks->launch_aux(aa, (int)std::min<int64_t>((N + 255) / 256, (int64_t)c->num_sms * 8), s);
             c->launches++;
+        } else if (atomics && !direct) {
+            PhaseScope ps(c, PH_AUX);
+            CK(cudaMemsetAsync(du, 0, (size_t)N * q * 8, s));
         }
         ea.aux = c->aux;
     } else if (atomics) {
         PhaseScope ps(c, PH_DSS);
         CK(cudaMemsetAsync(du, 0, (size_t)N * q * 8, s));
     }
+    if (direct) {
+        // the low-storage register must hold A_i S'_{i-1}: left so by the previous stage's sweep, else the accumulation
+        // restarts from zero (first stage of a step, A_1 = 0; or a stand-alone stage of jx_bench_rhs)
+        if (!(c->acc_ready && c->acc_A == upd.A)) {
+            PhaseScope ps(c, PH_AUX);
+            CK(cudaMemsetAsync(acc, 0, (size_t)N * q * 8, s));
+        }
+        c->acc_ready = false;
+        if (c->have_halo && c->n_ifn > 0) {
+            PhaseScope ps(c, PH_HALO);
+            k_if_save_zero<<<nblk(c->n_ifn * q, 256), 256, 0, s>>>(acc, N, q, c->d_ifn, c->n_ifn, c->d_ifbase);
+            c->launches++;
+        }
+    }
+    ea.du = acc;
+    auto restore_iface = [&]() {
+        if (direct && c->have_halo && c->n_ifn > 0) {
+            k_if_restore<<<nblk(c->n_ifn * q, 256), 256, 0, s>>>(acc, N, q, c->d_ifn, c->n_ifn, c->d_ifbase);
+            c->launches++;
+        }
+    };
     ea.glist = nullptr; ea.gctr = nullptr; ea.nlist = 0; ea.reserve_sms = 0; ea.exit_ctr = nullptr; ea.exit_budget = 0;
     const bool split = atomics && c->have_halo && c->split_ready && c->n_iface > 0 && ks->has_dyn && E > 0;
     if (split) {
@@ -1022,27 +1074,45 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
         const int per_sm = std::max(1, ks->max_blocks_per_sm());
         const int cap = c->num_sms * per_sm;
         CK(cudaMemsetAsync(c->d_gctr, 0, 4 * sizeof(int), s));
+        // the AV viscous pass (k_visc_quad) walks the same lists behind each inviscid launch
+        ViscArgs va;
+        va.rec = c->rec_visc; va.out_el = c->rhs_el_visc; va.nv = 0;
+        if (c->lvisc && ks->launch_visc)
+            for (int e = 0; e < q && e < 8; ++e)
+                if (c->visc[e] != 0.0) va.ve[va.nv++] = e;
+        for (int i = va.nv; i < 8; ++i) va.ve[i] = 0;
+        const int vper = va.nv > 0 ? std::max(1, ks->visc_max_blocks()) : 1;
         {
             PhaseScope ps(c, PH_ELEM);
             ea.glist = c->d_glist; ea.nlist = c->n_iface; ea.gctr = c->d_gctr; ea.reserve_sms = 0;
             ks->launch_elem(ea, std::min(c->n_iface, cap), s);
+            if (va.nv > 0) {
+                ks->launch_visc(ea, va, std::min(c->n_iface, c->num_sms * vper), s);
+                c->launches++;
+            }
             CK(cudaEventRecord(c->ev_fork, s));
             ea.glist = c->d_glist + c->n_iface; ea.nlist = c->n_inner; ea.gctr = c->d_gctr + 1;
             ea.reserve_sms = std::min(c->overlap_sms, c->num_sms / 2);
             // the launch carries reserve_sms * per_sm surplus CTAs; only that many may leave a reserved SM unworked
             ea.exit_ctr = c->d_gctr + 2; ea.exit_budget = ea.reserve_sms * per_sm;
             ks->launch_elem(ea, (int)std::min<int64_t>((int64_t)c->n_inner + (int64_t)ea.reserve_sms * per_sm, cap), s);
+            if (va.nv > 0) {
+                ea.exit_ctr = c->d_gctr + 3; ea.exit_budget = ea.reserve_sms * vper;
+                ks->launch_visc(ea, va, (int)std::min<int64_t>((int64_t)c->n_inner + (int64_t)ea.reserve_sms * vper, (int64_t)c->num_sms * vper), s);
+                c->launches++;
+            }
             c->launches += 2;
         }
         CK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-        int rc = assemble(c, du, c->stream2);                            // DSS_global_RHS!, rhs.jl:690
+        int rc = assemble(c, acc, c->stream2);                           // DSS_global_RHS!, rhs.jl:690
         if (rc) return rc;
         CK(cudaEventRecord(c->ev_join, c->stream2));
         {
             PhaseScope ps(c, PH_HALO);                                   // what is left exposed after the interior launch
             CK(cudaStreamWaitEvent(s, c->ev_join, 0));
+            restore_iface();
         }
-        if (upd.kind == 1) stage_update();
+        if (upd.kind != 0) stage_update();
         CK(cudaGetLastError());
         return JX_OK;
     }
@@ -1080,8 +1150,9 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     if (c->have_halo) {                                                  // DSS_global_RHS!, rhs.jl:690
         {
             PhaseScope ps(c, PH_HALO);
-            int rc = assemble(c, du, s);
+            int rc = assemble(c, acc, s);
             if (rc) return rc;
+            restore_iface();
         }
         if (!fold_minv) {
             PhaseScope ps(c, PH_UPDATE);
@@ -1089,7 +1160,7 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
             c->launches++;
         }
     }
-    if (upd.kind == 1) stage_update();
+    if (upd.kind != 0) stage_update();
     CK(cudaGetLastError());
     return JX_OK;
 }
@@ -1184,7 +1255,8 @@ extern "C" int jx_step(jx_ctx *c, int scheme, double t, double dt, int nsteps) {
         auto one_step = [&]() -> int {
             for (int i = 0; i < 5; ++i) {
                 StageUpdate upd;
-                upd.kind = 1; upd.A = CK_A[i]; upd.B = CK_B[i]; upd.dt = dt; upd.first = (i == 0);
+                upd.kind = direct_ok(c) ? 2 : 1; upd.A = CK_A[i]; upd.B = CK_B[i]; upd.dt = dt; upd.first = (i == 0);
+                upd.Anext = CK_A[(i + 1) % 5];
                 const int r = rhs_core(c, c->u, c->du, upd);
                 if (r) return r;
             }
@@ -1319,7 +1391,7 @@ extern "C" int jx_bench_rhs(jx_ctx *c, int n, int fused_stage, float *total_ms, 
     c->phase_timing = phase_ms != nullptr;
     StageUpdate upd;
     if (fused_stage) {   // a dt = 0 CK2N54 stage: full stage traffic, state unchanged
-        upd.kind = 1; upd.A = CK_A[1]; upd.B = CK_B[1]; upd.dt = 0.0; upd.first = 0;
+        upd.kind = direct_ok(c) ? 2 : 1; upd.A = CK_A[1]; upd.B = CK_B[1]; upd.dt = 0.0; upd.first = 0; upd.Anext = CK_A[1];
     }
     int rc = JX_OK;
     // CUDA graph path (no per-phase events): one RHS evaluation -- kernels, NCCL send/recv groups, copies -- is

@@ -549,51 +549,63 @@ static __global__ void k_node_aux(const __grid_constant__ AuxArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Atomics mode: the 2N low-storage stage update (tmp = A*tmp + dt*du, u += B*tmp; k_lsrk_update's expressions), the
-// zero-fill of du for the NEXT evaluation's scatter and the next evaluation's per-node equation of state in ONE sweep
-// over the nodes: the next rhs! then starts at the Dirichlet projection (which re-evaluates aux at the nodes it
-// changes) and the element kernel -- k_node_aux and one full pass over du leave the stage.
+// Atomics mode, 2N low-storage schemes (Williamson form S_i = A_i S_{i-1} + dt F(u), u += B_i S_i): the element kernels
+// RED.ADD their mass-scaled contributions DIRECTLY into the low-storage register, kept as S' = S / dt and pre-scaled by
+// the stage's A_i (S'_i = A_i S'_{i-1} + F).  What is left of the stage is ONE sweep:
+//     u += (B_i dt) S'_i;   S' <- A_{i+1} S'_i (exact zeros when A_{i+1} = 0: first stage of the next step);   aux = EOS(u)
+// 168 B per node instead of 288 (k_lsrk_update + k_node_aux with its zero-fill): no du array, no zero-fill, no separate
+// equation-of-state pass.  The next rhs! starts at the Dirichlet projection, which re-evaluates aux at the nodes it changes.
+// (Sums differ from tmp = A tmp + dt du by the association of the dt factor: inside the bars of the unordered mode.)
 // ------------------------------------------------------------------------------------------
 struct StageArgs {
-    double *u, *tmp, *du;
+    double *u, *acc;      // state and low-storage register S'
     const double *qe;
-    double *aux;      // [NAUX][npoin] or nullptr
+    double *aux;          // [NAUX][npoin]
     int64_t npoin;
-    double A, B, dt;
-    int first;
+    double Bdt, Anext;
     Phys phys;
 };
 
 template <class EQ>
-static __global__ void __launch_bounds__(256) k_stage_fused(const __grid_constant__ StageArgs a) {
+static __global__ void __launch_bounds__(256) k_stage_direct(const __grid_constant__ StageArgs a) {
     constexpr int NEQ = EQ::NEQ;
     for (int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ip < a.npoin; ip += (int64_t)gridDim.x * blockDim.x) {
-        double d[NEQ], tm[NEQ], q[NEQ], qe[NEQ + 1];
+        double s[NEQ], q[NEQ], qe[NEQ + 1];
 #pragma unroll
-        for (int e = 0; e < NEQ; ++e) d[e] = __ldcs(a.du + (size_t)e * a.npoin + ip);
-#pragma unroll
-        for (int e = 0; e < NEQ; ++e) tm[e] = a.first ? 0.0 : __ldcs(a.tmp + (size_t)e * a.npoin + ip);
+        for (int e = 0; e < NEQ; ++e) s[e] = a.acc[(size_t)e * a.npoin + ip];
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) q[e] = a.u[(size_t)e * a.npoin + ip];
 #pragma unroll
         for (int e = 0; e <= NEQ; ++e) qe[e] = (EQ::NEEDS_QE && EQ::HAS_AUX && (e == NEQ || ((EQ::AUX_MASK >> e) & 1u))) ? a.qe[(size_t)e * a.npoin + ip] : 0.0;
 #pragma unroll
         for (int e = 0; e < NEQ; ++e) {
-            tm[e] = a.first ? a.dt * d[e] : a.A * tm[e] + a.dt * d[e];
-            q[e] = q[e] + a.B * tm[e];
-            __stcs(a.tmp + (size_t)e * a.npoin + ip, tm[e]);
+            q[e] = q[e] + a.Bdt * s[e];
             a.u[(size_t)e * a.npoin + ip] = q[e];
-            a.du[(size_t)e * a.npoin + ip] = 0.0;
+            a.acc[(size_t)e * a.npoin + ip] = a.Anext == 0.0 ? 0.0 : a.Anext * s[e];
         }
         if constexpr (EQ::HAS_AUX) {
-            if (a.aux) {
-                double ax[EQ::NAUX > 0 ? EQ::NAUX : 1];
-                EQ::aux(a.phys, q, qe, ax);
+            double ax[EQ::NAUX > 0 ? EQ::NAUX : 1];
+            EQ::aux(a.phys, q, qe, ax);
 #pragma unroll
-                for (int x = 0; x < EQ::NAUX; ++x) a.aux[(size_t)x * a.npoin + ip] = ax[x];
-            }
+            for (int x = 0; x < EQ::NAUX; ++x) a.aux[(size_t)x * a.npoin + ip] = ax[x];
         }
     }
+}
+
+// interface / periodic-twin nodes under the direct accumulation: their share of S' is set aside and zeroed before the
+// element kernels, so that the exchange sums pure contributions, and added back afterwards (thread = (node of the list, equation))
+static __global__ void k_if_save_zero(double *a, int64_t npoin, int m, const int64_t *idx, int64_t len, double *base) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= len * m) return;
+    const size_t o = (size_t)(t % m) * npoin + idx[t / m];
+    base[t] = a[o];
+    a[o] = 0.0;
+}
+static __global__ void k_if_restore(double *a, int64_t npoin, int m, const int64_t *idx, int64_t len, const double *base) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= len * m) return;
+    const size_t o = (size_t)(t % m) * npoin + idx[t / m];
+    a[o] = base[t] + a[o];
 }
 
 // cp.async (LDGSTS) helpers

@@ -44,7 +44,7 @@ template <class EQ>
 void launch_stage_t(const StageArgs &a, int grid, cudaStream_t s) {
     if (a.npoin <= 0) return;
     (void)grid;   // one node per thread: 1.07 ms at 25 M nodes against 1.5-1.7 ms for a persistent grid (scripts/micro/stage_bench.cu)
-    k_stage_fused<EQ><<<(unsigned)((a.npoin + 255) / 256), 256, 0, s>>>(a);
+    k_stage_direct<EQ><<<(unsigned)((a.npoin + 255) / 256), 256, 0, s>>>(a);
 }
 
 template <int NEQ>
@@ -198,6 +198,43 @@ KernelSet make_team_visc_set(int eq_id, int lpert, int jxpow, int variant) {
     ks.visc_prepare = &V::prepare;
     ks.visc_group_bytes = V::C::GROUP_BYTES; ks.visc_zid_off = V::C::ZID_OFF;
     ks.visc_fid_off = V::C::FID_OFF;
+    ks.visc_layout = 1;
+    ks.retile_visc = [](const ViscRetileArgs &a, unsigned grid, cudaStream_t s) { k_retile_visc<<<grid, 256, 0, s>>>(a); };
+    return ks;
+}
+
+// variant 13: the inviscid team kernel followed by k_visc_quad (four warps per pair, node-parallel node-local step)
+template <int NGL, class EQ>
+struct ViscQuadKernel {
+    using C = ViscQuadCfg<NGL, EQ>;
+    static cudaError_t prepare() {
+        cudaError_t e = cudaFuncSetAttribute(k_visc_quad<NGL, EQ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_visc_quad<NGL, EQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        return e;
+    }
+    static int max_blocks() {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_visc_quad<NGL, EQ, 2>, C::NT, C::SMEM_BYTES);
+        return nb;
+    }
+    static void launch(const ElemArgs &a, const ViscArgs &v, int grid, cudaStream_t s) {
+        if (!a.atomics) k_visc_quad<NGL, EQ, 0><<<grid, C::NT, C::SMEM_BYTES, s>>>(a, v);
+        else k_visc_quad<NGL, EQ, 2><<<grid, C::NT, C::SMEM_BYTES, s>>>(a, v);
+    }
+};
+
+template <int NGL, class EQ, int ZW, int PW>
+KernelSet make_team_visc_quad_set(int eq_id, int lpert, int jxpow, int variant) {
+    KernelSet ks = make_team_set<NGL, EQ, ZW, PW>(eq_id, lpert, jxpow, variant);
+    using V = ViscQuadKernel<NGL, EQ>;
+    ks.lvisc = 1;
+    ks.has_dyn = 1;                       // the viscous pass walks the same pair lists (ElemArgs::glist) as the inviscid launch
+    ks.launch_visc = &V::launch;
+    ks.visc_max_blocks = &V::max_blocks;
+    ks.visc_prepare = &V::prepare;
+    ks.visc_group_bytes = V::C::GROUP_BYTES; ks.visc_zid_off = V::C::ID_OFF; ks.visc_fid_off = V::C::ID_OFF;
+    ks.visc_layout = 2;
+    ks.retile_visc = [](const ViscRetileArgs &a, unsigned grid, cudaStream_t s) { k_retile_visc_quad<<<grid, 256, 0, s>>>(a); };
     return ks;
 }
 

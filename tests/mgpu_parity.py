@@ -50,7 +50,8 @@ def main():
         uo = [u.copy() for u in us]
         duo = [np.zeros_like(u) for u in us]
         run.rhs(duo, uo, 0.0)
-        inputs = {"SOL_VARS_TYPE": "TOTAL", "lsource": True, "lvisc": lvisc, "mu": MU3, "dt": 0.4, "ode_solver": "CarpenterKennedy2N54"}
+        inputs = {"SOL_VARS_TYPE": "TOTAL", "lsource": True, "lvisc": lvisc, "mu": MU3, "dt": 0.05 if big else 0.4,   # 39 m node spacing at C4
+                  "ode_solver": "CarpenterKennedy2N54"}
         p = jrhs.params_setup(sems[rank], qes[rank], inputs, device=local, rank=rank, nranks=world, nccl_uid=box[0],
                               pow_mode=1, dss_mode=dss, elem_kernel=variant, overlap=overlap)
         split = p.ctx.split_info()

@@ -286,10 +286,12 @@ def test_team_kernel_atomics(variant, lpert):
         assert pn <= 1e-12 and l2 <= 1e-10, (variant, lpert, e, pn, l2)
 
 
+@pytest.mark.parametrize("variant", [9, 13])
 @pytest.mark.parametrize("lpert", [False, True])
 @pytest.mark.parametrize("mu", [MU3, [0.0, 125.0, 0.0, 60.0, 125.0], [5.0, 125.0, 125.0, 125.0, 125.0]])
-def test_visc_team_kernel_bit_exact(lpert, mu):
-    """k_visc_team: the AV viscous term of 3D nop-4 elements as a warp-team pass of its own (line owners with all nine metric
+def test_visc_team_kernel_bit_exact(lpert, mu, variant):
+    """Variant 13 = k_visc_quad (four warps per pair, node-parallel node-local step, node-ordered records); variant 9 =
+    k_visc_team: the AV viscous term of 3D nop-4 elements as a warp-team pass of its own (line owners with all nine metric
     terms of their nodes, metric-free plane lanes) behind the inviscid team kernel; same order of every sum as the reference.
     1287 elements: ragged last pair, several pairs per CTA.  The mu vectors exercise the skipping of inviscid equations
     (4, 3 and 5 viscous equations: uneven halves)."""
@@ -301,7 +303,7 @@ def test_visc_team_kernel_bit_exact(lpert, mu):
     run.rhs(dus, ub, 0.0)
     inputs = dict(_inputs(lpert, True, 3), mu=mu)
     for dss in (0, 1):
-        p = jrhs.params_setup(sems[0], qes[0], inputs, pow_mode=1, dss_mode=dss, elem_kernel=9)
+        p = jrhs.params_setup(sems[0], qes[0], inputs, pow_mode=1, dss_mode=dss, elem_kernel=variant)
         try:
             u, du = us[0].copy(), np.empty_like(us[0])
             jrhs.rhs_bang(du, u, p, 0.0)
@@ -367,7 +369,7 @@ def test_kernel_variant_requires_its_record_layout_before_upload():
     p = jrhs.params_setup(sems[0], qes[0], _inputs(False, False, 3), pow_mode=1, dss_mode=0, elem_kernel=0)
     try:
         with pytest.raises(capi.JexError) as ei:
-            p.ctx.set_option(capi.JX_OPT_ELEM_KERNEL, 9)
+            p.ctx.set_option(capi.JX_OPT_ELEM_KERNEL, capi.JX_ELEM_GENERIC)      # per-element records (layout 0)
         assert ei.value.code == capi.JX_ESTATE
         with pytest.raises(capi.JexError) as ei:
             p.ctx.set_option(capi.JX_OPT_ELEM_KERNEL, 3)        # a round-1 pencil variant: no longer compiled

@@ -119,13 +119,14 @@ def test_c3_density_current_box_at_stated_size():
 def test_c4_abl_box_at_stated_size_one_gpu():
     """BASELINE configs[3] at its stated size on one GPU: 3D, 64 x 64 x 24 elements, nop 4, periodic in x and y (the twins
     are summed through the assembler's self lists, restructure_for_periodicity.jl:1387-1577 / mpi_communications.jl:99-112),
-    free-slip top and bottom, AV viscous term: one rhs! and one CK2N54 step, bit-exact against the oracle.  (The 2/4/8-rank
-    NCCL runs of the same mesh: tests/mgpu_parity.py cases 4 and 5, profiles/.)"""
+    free-slip top and bottom, AV viscous term: one rhs! and the first CK2N54 stages of a step (JX_C4_STEPS, default 0: the
+    oracle needs about 25 s per evaluation at this size), bit-exact against the oracle.  (The 2/4/8-rank NCCL runs of the same
+    mesh with a whole step: tests/mgpu_parity.py cases 4 and 5, profiles/.)"""
     from helpers import MU3, box3d
     nel = tuple(int(x) for x in os.environ.get("JX_C4_NEL", "64,64,24").split(","))
     spec = box3d(nel, 4, warp=0.05, periodic=(True, True, False), L=(10000.0, 10000.0, 3750.0))
-    duo, ue, du, ug, variant = _oracle_and_gpu(spec, MU3, 1, 0.05)
-    assert variant == 9, variant       # the warp-team kernels (inviscid + viscous pass) carry this configuration
+    duo, ue, du, ug, variant = _oracle_and_gpu(spec, MU3, int(os.environ.get("JX_C4_STEPS", "0")), 0.05)
+    assert variant == 13, variant      # the warp-team kernels (k_elem_team + k_visc_quad) carry this configuration
     assert np.isfinite(du).all() and np.isfinite(ug).all()
     assert np.array_equal(du, duo), rel_err_per_node(du, duo)
     assert np.array_equal(ug, ue), rel_err_per_node(ug, ue)
