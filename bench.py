@@ -239,8 +239,6 @@ def workload_name(a):
 
 
 def elem_kernel_name(ctx_variant, a):
-    if a.visc and ctx_variant == 9:
-        return "k_elem_team + k_visc_team (inviscid warp-team kernel followed by the AV viscous warp-team pass)"
     if a.visc and ctx_variant == 13:
         return "k_elem_team + k_visc_quad (inviscid warp-team kernel followed by the four-warp AV viscous pass)"
     return {9: "k_elem_team (fused flux + divergence per element pair; variant 9)",
@@ -475,7 +473,7 @@ def main():
     if world == 1 and not a.no_cpu:
         build_oracle_only()
         t0 = time.perf_counter()
-        reps = 5
+        reps = 10
         dofs, dt = cpu_sample(a.cpu_nel, a.nop, a.visc, reps, a.config)
         line["cpu_baseline"] = {"value": dofs / dt / 1e9, "unit": "GDOF/s", "cores": 1, "kind": "port",
                                 "sample": f"oracle/jexref.c rhs! + stage update on {dofs} DOF of the same discretisation "

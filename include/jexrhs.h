@@ -63,8 +63,8 @@ typedef struct jx_ctx jx_ctx;
 #define JX_OPT_ELEM_KERNEL 3   /* element-kernel variant: JX_ELEM_AUTO (default) picks the fastest exact-order kernel that
                                   exists for the configuration (3D inviscid nop 2/4: the warp-team kernel, else the generic
                                   one); JX_ELEM_GENERIC forces the generic thread-per-node kernel; 8 / 9 name the warp-team kernel
-                                  (one / two plane warps; with AV: followed by k_visc_team), 13 = 9 followed by the four-warp viscous pass
-                                  k_visc_quad (the AV default), 12 the three-role pencil kernel of nop 7 (opt-in).
+                                  (one / two plane warps), 13 = 9 followed by the four-warp viscous pass k_visc_quad (the default with AV),
+                                  12 the three-role pencil kernel of nop 7 (opt-in).
                                   All variants keep the reference's order of every sum: bit-identical results. */
 #define JX_ELEM_AUTO 0
 #define JX_ELEM_GENERIC (-1)
@@ -107,6 +107,16 @@ int jx_upload_mesh(jx_ctx *, const int64_t *connijk, const double *coords, const
  * so the 10 (5) element-sized host arrays need not exist.  Results are bit-identical to the host arrays of the oracle. */
 int jx_upload_mesh_coords(jx_ctx *, const int64_t *connijk, const double *coords, const double *dpsi, const double *omega,
                           const double *Minv, const double *qe);
+/* Minv == NULL in jx_upload_mesh_coords: the diagonal mass matrix is built on the device as well -- replaces matrix_wrapper's
+ * build_mass_matrix! + DSS_mass! + DSS_global_mass! + Minv = 1 ./ M (src/kernel/infrastructure/element_matrices.jl:173-214,
+ * 593-617, 1160-1174, 1557-1559): M[ip] = sum over elements ascending of (w_i*w_j)*w_k*Je, summed across the ranks through the
+ * lists of jx_upload_halo (upload them before the first evaluation), inverted.  Bit-identical to the host arrays of the oracle.
+ * jx_get_minv returns the assembled M^-1 (Float64[npoin]). */
+int jx_get_minv(jx_ctx *, double *Minv);
+/* replaces: conformity4ncf_q! (src/kernel/Adaptivity/Projection.jl:2919-2970; params_setup.jl:259-297), the conditioning of the
+ * initial state that gives shared / periodic-twin nodes one value:  q <- Minv * DSS_global(wJac * q) on the neqs columns of the
+ * resident state (which = 0, after jx_set_state) or of the reference state qe (which = 1).  Needs the device-built mass. */
+int jx_condition_state(jx_ctx *, int which);
 
 /* replaces: params.mesh.poin_in_bdy_face / poin_in_bdy_edge, params.metrics.nx/ny/nz, bdy_face_type
  * (tags mapped to JX_BC_* kinds by the host).  3D arrays are [nfaces, ngl, ngl], 2D [nedges, ngl]. */

@@ -59,6 +59,8 @@ def lib():
     L.jx_upload_mesh.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp]
     L.jx_upload_mesh_coords.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.jx_upload_bcs.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    L.jx_get_minv.argtypes = [vp, vp]
+    L.jx_condition_state.argtypes = [vp, ctypes.c_int]
     L.jx_upload_halo.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.jx_set_state.argtypes = [vp, vp]
     L.jx_get_state.argtypes = [vp, vp]
@@ -148,9 +150,19 @@ class Context:
 
     def upload_mesh_coords(self, connijk, coords, dpsi, omega, Minv, qe):
         """jx_upload_mesh with the metric terms built on the device from the coordinates."""
-        c, x, d, o, mi = i64(connijk), f64(coords), f64(dpsi), f64(omega), f64(Minv)
+        c, x, d, o = i64(connijk), f64(coords), f64(dpsi), f64(omega)
+        mi = f64(Minv) if Minv is not None else None        # None: the mass matrix is built on the device too
         q = f64(qe) if qe is not None else None
         self._ck(lib().jx_upload_mesh_coords(self._h, _ptr(c), _ptr(x), _ptr(d), _ptr(o), _ptr(mi), _ptr(q)))
+
+    def get_minv(self):
+        mi = np.empty(self.npoin)
+        self._ck(lib().jx_get_minv(self._h, _ptr(mi)))
+        return mi
+
+    def condition_state(self, which=0):
+        """conformity4ncf_q! on the resident state (0) or the reference state (1); needs upload_mesh_coords(Minv=None)."""
+        self._ck(lib().jx_condition_state(self._h, int(which)))
 
     def upload_bcs(self, poin_in_bdy_face, nx, ny, nz, kinds):
         p = i64(poin_in_bdy_face)

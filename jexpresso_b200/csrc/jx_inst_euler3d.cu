@@ -14,18 +14,16 @@ namespace jx {
     JX_TSET(NGL, ZW, PW, VAR, false, false), JX_TSET(NGL, ZW, PW, VAR, false, true), JX_TSET(NGL, ZW, PW, VAR, true, false), \
     JX_TSET(NGL, ZW, PW, VAR, true, true)
 
-#define JX_TVSET(PERT, POW) make_team_visc_set<5, EulerTheta<3, PERT, POW>, 2, 2>(JX_EQ_EULER_THETA, PERT, POW, 9)
 #define JX_TVQSET(PERT, POW) make_team_visc_quad_set<5, EulerTheta<3, PERT, POW>, 2, 2>(JX_EQ_EULER_THETA, PERT, POW, 13)
 #define JX_TRISET(PERT, POW) make_tri_set<8, EulerTheta<3, PERT, POW>>(JX_EQ_EULER_THETA, PERT, POW, 12)
 
 const KernelSet *lookup_euler_theta_3d(int ngl, int lpert, int jxpow, int lvisc, int variant) {
 #ifdef JX_MIN_BUILD   // kernel experiments: nop 4, TOTAL, jx_pow only -- generic, team (9), tri (12), viscous team pass
     static const KernelSet table[] = {JX_SET(5, false, true, false), JX_SET(5, false, true, true), JX_TSET(5, 2, 2, 9, false, true),
-                                      JX_SET(8, false, true, false), JX_TRISET(false, true), JX_TVSET(false, true), JX_TVQSET(false, true)};
+                                      JX_SET(8, false, true, false), JX_TRISET(false, true), JX_TVQSET(false, true)};
 #else
     static const KernelSet table[] = {JX_ROW(3), JX_ROW(5), JX_ROW(6), JX_ROW(8), JX_TROW(3, 3, 1, 8), JX_TROW(5, 2, 1, 8), JX_TROW(5, 2, 2, 9),
                                       JX_TRISET(false, false), JX_TRISET(false, true), JX_TRISET(true, false), JX_TRISET(true, true),
-                                      JX_TVSET(false, false), JX_TVSET(false, true), JX_TVSET(true, false), JX_TVSET(true, true),
                                       JX_TVQSET(false, false), JX_TVQSET(false, true), JX_TVQSET(true, false), JX_TVQSET(true, true)};
 #endif
     for (const KernelSet &k : table)

@@ -26,14 +26,14 @@ struct KernelSet {
     // atomics mode, 2N schemes: u += B dt S', S' <- A_next S', next aux in one sweep (k_stage_direct) behind element kernels
     // that accumulate into S' directly; set for the kernels with launch_aux
     void (*launch_stage)(const StageArgs &, int grid, cudaStream_t) = nullptr;
-    // AV viscous term as a pass of its own (k_visc_team) behind an inviscid element kernel: its launcher and the layout of
+    // AV viscous term as a pass of its own (k_visc_quad) behind an inviscid element kernel: its launcher and the layout of
     // its pair records (nullptr: the element kernel itself carries the viscous pass, or lvisc = 0)
     void (*launch_visc)(const ElemArgs &, const ViscArgs &, int grid, cudaStream_t) = nullptr;
     int (*visc_max_blocks)() = nullptr;
     cudaError_t (*visc_prepare)() = nullptr;
     void (*retile_visc)(const ViscRetileArgs &, unsigned grid, cudaStream_t) = nullptr;   // builds the viscous pair records
     int visc_group_bytes = 0, visc_zid_off = 0, visc_fid_off = 0;
-    int visc_layout = 0;                                        // 0: no viscous records; 1: k_visc_team; 2: k_visc_quad (node ordered)
+    int visc_layout = 0;                                        // 0: no viscous records; 2: k_visc_quad (node ordered)
     // rec_layout 5 (element-group records of the team kernels): bytes per group and stream / id offsets
     int group_bytes = 0, group_nt = 0, zid_off = 0, fid_off = 0, z_off = 0, w_off = 0, wf_off = 0;
     int has_dyn = 0;                                            // launch_elem honours ElemArgs::glist/gctr (interface-first split)

@@ -1234,6 +1234,47 @@ static __global__ void k_build_metric(MetricBuildArgs a) {
 }
 
 // interface-first split: nodes named by the assembler lists, then the element groups whose records name one of them
+// ------------------------------------------------------------------------------------------
+// Setup on the device: diagonal mass matrix and IC conditioning.
+//   DSS_mass! (element_matrices.jl:593-617) of build_mass_matrix! (:173-214, psi = identity at the LGL points):
+//       M[ip] = sum over (element ascending, local node ascending) of (w_m*w_n)*w_o * Je          [2D: w_m*w_n * Je]
+//   conformity4ncf_q! (Adaptivity/Projection.jl:2919-2970):  q[ip] <- Minv[ip] * DSS(wJac * q[ip]),  wJac = (w_i*w_j)*w_k*Je
+// Both walk the node -> (element, local) CSR, which is sorted in the reference's visiting order.
+// ------------------------------------------------------------------------------------------
+static __global__ void k_mass_weight(const double *Je, const double *omega, int64_t nelem, int ngl, int nsd, double *w) {
+    const int np = nsd == 3 ? ngl * ngl * ngl : ngl * ngl;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= nelem * np) return;
+    const int l = (int)(tid / nelem);
+    const int i = l % ngl, j = (l / ngl) % ngl, k = l / (ngl * ngl);
+    const double wij = omega[i] * omega[j];
+    const double w3 = nsd == 3 ? wij * omega[k] : wij;
+    w[tid] = w3 * Je[tid];
+}
+// neq == 0: M[ip] = sum of weights;  neq > 0: out[e][ip] = sum of (weight * q[e][ip]) for the first neq columns of q
+static __global__ void k_mass_gather(const int64_t *ptr, const uint32_t *idx, const double *w, int64_t nelem, int np, int64_t npoin,
+                                     int neq, const double *q, double *out) {
+    const int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= npoin) return;
+    const int64_t p0 = ptr[ip], p1 = ptr[ip + 1];
+    if (neq == 0) {
+        double s = 0.0;
+        for (int64_t p = p0; p < p1; ++p) { const uint32_t x = idx[p]; s += w[(size_t)(x / np) + (size_t)nelem * (x % np)]; }
+        out[ip] = s;
+    } else {
+        for (int e = 0; e < neq; ++e) {
+            const double qv = q[(size_t)e * npoin + ip];
+            double s = 0.0;
+            for (int64_t p = p0; p < p1; ++p) { const uint32_t x = idx[p]; s += w[(size_t)(x / np) + (size_t)nelem * (x % np)] * qv; }
+            out[(size_t)e * npoin + ip] = s;
+        }
+    }
+}
+static __global__ void k_invert(double *a, int64_t n) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) a[t] = 1.0 / a[t];
+}
+
 static __global__ void k_mark_nodes(uint8_t *mask, const int64_t *idx, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) mask[idx[i]] = 1;

@@ -167,42 +167,6 @@ KernelSet make_tri_set(int eq_id, int lpert, int jxpow, int variant) {
     return ks;
 }
 
-// AV viscous pass of its own (k_visc_team) attached to an inviscid team set: variant 9 with lvisc = 1
-template <int NGL, class EQ>
-struct ViscKernel {
-    using C = ViscTeamCfg<NGL, EQ>;
-    static cudaError_t prepare() {
-        cudaError_t e = cudaFuncSetAttribute(k_visc_team<NGL, EQ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_visc_team<NGL, EQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
-        return e;
-    }
-    static int max_blocks() {
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_visc_team<NGL, EQ, 2>, C::NT, C::SMEM_BYTES);
-        return nb;
-    }
-    static void launch(const ElemArgs &a, const ViscArgs &v, int grid, cudaStream_t s) {
-        if (!a.atomics) k_visc_team<NGL, EQ, 0><<<grid, C::NT, C::SMEM_BYTES, s>>>(a, v);
-        else k_visc_team<NGL, EQ, 2><<<grid, C::NT, C::SMEM_BYTES, s>>>(a, v);
-    }
-};
-
-template <int NGL, class EQ, int ZW, int PW>
-KernelSet make_team_visc_set(int eq_id, int lpert, int jxpow, int variant) {
-    KernelSet ks = make_team_set<NGL, EQ, ZW, PW>(eq_id, lpert, jxpow, variant);
-    using V = ViscKernel<NGL, EQ>;
-    ks.lvisc = 1;
-    ks.has_dyn = 0;                       // the viscous pass walks all pairs: no interface-first split
-    ks.launch_visc = &V::launch;
-    ks.visc_max_blocks = &V::max_blocks;
-    ks.visc_prepare = &V::prepare;
-    ks.visc_group_bytes = V::C::GROUP_BYTES; ks.visc_zid_off = V::C::ZID_OFF;
-    ks.visc_fid_off = V::C::FID_OFF;
-    ks.visc_layout = 1;
-    ks.retile_visc = [](const ViscRetileArgs &a, unsigned grid, cudaStream_t s) { k_retile_visc<<<grid, 256, 0, s>>>(a); };
-    return ks;
-}
-
 // variant 13: the inviscid team kernel followed by k_visc_quad (four warps per pair, node-parallel node-local step)
 template <int NGL, class EQ>
 struct ViscQuadKernel {

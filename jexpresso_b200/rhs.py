@@ -58,7 +58,7 @@ class Params:
 
 
 def params_setup(sem, qe, inputs, *, device=0, rank=0, nranks=1, nccl_uid=None, eqs="CompEuler", phys=None,
-                 dss_mode=0, pow_mode=1, elem_kernel=0, overlap=0, device_metrics=False):
+                 dss_mode=0, pow_mode=1, elem_kernel=0, overlap=0, device_metrics=False, device_mass=False):
     """Upload one rank's SEM bundle (mesh, metrics, basis, M^-1, reference state, boundary and
     interface lists) to its GPU and return the ``params`` handle ``rhs_bang`` takes."""
     m = sem.mesh
@@ -78,8 +78,9 @@ def params_setup(sem, qe, inputs, *, device=0, rank=0, nranks=1, nccl_uid=None, 
         ctx.set_option(capi.JX_OPT_ELEM_KERNEL, elem_kernel)
         ctx.set_option(capi.JX_OPT_OVERLAP, overlap)
         ctx.set_problem(m.nsd, m.ngl, neqs, m.nelem, m.npoin, eq_id, lpert, bool(inputs.get("lsource", False)), lvisc, mu, phys)
-        if device_metrics:      # build_metric_terms! on the device (jx_upload_mesh_coords): sem.metrics is not read
-            ctx.upload_mesh_coords(m.connijk, m.coords, sem.basis["dpsi"], sem.basis["omega"], sem.Minv, qe)
+        if device_metrics or device_mass:   # build_metric_terms! on the device (jx_upload_mesh_coords): sem.metrics is not read;
+            # device_mass: neither is sem.Minv -- the mass matrix is built, assembled over the halo lists and inverted on the device
+            ctx.upload_mesh_coords(m.connijk, m.coords, sem.basis["dpsi"], sem.basis["omega"], None if device_mass else sem.Minv, qe)
         else:
             ctx.upload_mesh(m.connijk, m.coords, sem.metric_list, sem.basis["dpsi"], sem.basis["omega"], sem.Minv, qe)
         if m.poin_in_bdy_face.shape[0] > 0:

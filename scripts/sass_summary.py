@@ -51,9 +51,13 @@ print(f"| **library** | {len(counts)} | {tot['_total']} | " + " | ".join(str(tot
 print("\n## default kernels of the bench configuration (3D theta TOTAL, jx_pow, nop 4)\n")
 print("| kernel | instr | " + " | ".join(OPS) + " |")
 print("|---|---|" + "---|" * len(OPS))
-want = [r"k_elem_team<5, jx::EulerTheta<3, false, true>, 2, 2, 2, false>", r"k_elem_team<5, jx::EulerTheta<3, false, true>, 2, 0, 2, false>",
-        r"k_visc_team<5, jx::EulerTheta<3, false, true>, 2>", r"k_stage_fused<jx::EulerTheta<3, false, true>", r"k_node_aux<jx::EulerTheta<3, false, true>",
-        r"k_bc_dirichlet<jx::EulerTheta<3, false, true>", r"k_elem_node<3, 8, jx::EulerTheta<3, false, true>, false", r"k_gather<5>"]
+want = ["k_elem_team<5, jx::EulerTheta<3, false, true>, 2, 2, 2, false>", "k_elem_team<5, jx::EulerTheta<3, false, true>, 2, 2, 2, true>",
+        "k_elem_team<5, jx::EulerTheta<3, false, true>, 2, 0, 2, false>", "k_visc_quad<5, jx::EulerTheta<3, false, true>, 2>",
+        "k_visc_quad<5, jx::EulerTheta<3, false, true>, 0>", "k_visc_team<5, jx::EulerTheta<3, false, true>, 2>",
+        "k_stage_direct<jx::EulerTheta<3, false, true>", "k_node_aux<jx::EulerTheta<3, false, true>",
+        "k_bc_dirichlet<jx::EulerTheta<3, false, true>", "k_elem_node<3, 5, jx::EulerTheta<3, false, true>, true",
+        "k_elem_node<3, 8, jx::EulerTheta<3, false, true>, false", "k_elem_node<2, 6, jx::EulerTheta<2, false, true>, true",
+        "k_elem_tri<8, jx::EulerTheta<3, false, true>, 2>", "k_gather<5>"]
 for w in want:
     for k, c in counts.items():
         kk = k.replace("(int)", "").replace("(bool)0", "false").replace("(bool)1", "true")

@@ -71,7 +71,7 @@ def main():
         pn2, l22 = rel_err_per_node(ug, us2[rank])
         exact = bool(np.array_equal(du, duo[rank]) and np.array_equal(ug, us2[rank]))
         good = exact if dss == 0 else (pn <= 1e-12 and l2 <= 1e-10 and pn2 <= 1e-12 and l22 <= 1e-10)
-        if overlap:
+        if overlap and world <= 4:          # (with more ranks the small box has no interior pairs left: nothing to split)
             good = good and split[0] > 0 and split[1] > 0
         ok &= good
         print(f"[rank {rank}/{world}] nel={nel} periodic={periodic} visc={lvisc} dss={dss} kernel={variant} overlap={overlap} split={split}: rhs pn={pn:.2e} l2={l2:.2e} "
