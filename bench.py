@@ -30,7 +30,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "3D Euler nop=4 RHS GDOF/s"
 # algorithmic bytes per unique node of one RHS evaluation (3D, q=5, Float64 data,
@@ -116,7 +115,7 @@ class ClockSampler:
 def build_problem(nel, nop, lpert, rank, nranks, warp=0.05, periodic=False, config="c5"):
     """This rank's SEM bundle + conditioned IC.  c5: weak-scaling box (nel^3 elements per GPU); c2 / c3 / c4: the fixed
     meshes of BASELINE.json configs[1..3], partitioned over the ranks like the reference's _compute_xy_partition."""
-    from helpers import box2d, box3d
+    from jexpresso_b200.sem.problems import box2d, box3d
     from jexpresso_b200.sem import rtb_initial_state
     from jexpresso_b200.sem.scalable import conformity4ncf_q_rank, sem_setup_rank
     L = 10000.0
@@ -151,7 +150,7 @@ CK_A1, CK_B1 = -567301805773.0 / 1357537059087.0, 5161836677717.0 / 136120682923
 def cpu_sample(nel, nop, lvisc, reps, config="c5"):
     """Time the CPU oracle (port of the reference's rhs!) plus the 2N low-storage stage update on ONE core: an nel^3-element
     box of the same discretisation (c5), or the configuration's own mesh cut down to at most nel^nsd elements."""
-    from helpers import MU2, MU3, PHYS, box2d, box3d, euler_case
+    from jexpresso_b200.sem.problems import MU2, MU3, PHYS, box2d, box3d, euler_case
     from oracle import ref
     nsd = CONFIGS[config][0]
     if nsd == 2:
@@ -285,7 +284,7 @@ def main():
     import torch.distributed as dist
     from jexpresso_b200 import capi
     from jexpresso_b200 import rhs as jrhs
-    from helpers import MU2, MU3
+    from jexpresso_b200.sem.problems import MU2, MU3
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

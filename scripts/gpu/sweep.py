@@ -14,7 +14,6 @@ import numpy as np
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", ".."))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
@@ -30,7 +29,7 @@ def main():
     ap.add_argument("--check", action="store_true", help="compare every variant's du with the first variant's (deterministic DSS)")
     a = ap.parse_args()
     from bench import build_problem
-    from helpers import MU3
+    from jexpresso_b200.sem.problems import MU3
     from jexpresso_b200 import capi
     from jexpresso_b200 import rhs as jrhs
     t0 = time.perf_counter()
