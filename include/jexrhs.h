@@ -133,6 +133,8 @@ int jx_upload_halo(jx_ctx *, const int64_t *send_ptr, const int64_t *send_i, con
 /* state: u is the ODE state vector Float64[npoin*neqs], index (ieq-1)*npoin + ip (rhs.jl:29-47) */
 int jx_set_state(jx_ctx *, const double *u);
 int jx_get_state(jx_ctx *, double *u);
+/* du of the last jx_rhs / jx_bench_rhs(fused_stage = 0) evaluation.  jx_step does not produce it in the atomics mode: there the
+ * element kernels accumulate straight into the 2N low-storage register. */
 int jx_get_du(jx_ctx *, double *du);
 
 /* replaces: rhs!(du,u,params,time).  u_host != NULL: upload u first; du_host != NULL: download du after.

@@ -805,6 +805,9 @@ extern "C" int jx_upload_halo(jx_ctx *c, const int64_t *send_ptr, const int64_t 
     cudaSetDevice(c->device);
     free_halo(c);
     if (!send_ptr || !recv_ptr || !recvback_ptr) return fail(c, JX_EINVAL, "jx_upload_halo: null pointer array");
+    if (c->massw && c->have_mesh && !c->mass_pending)
+        return fail(c, JX_ESTATE, "the device-built mass matrix was already assembled without these lists: call jx_upload_halo "
+                    "before the first evaluation / jx_get_minv / jx_condition_state");
     const int R = c->nranks;
     const int64_t ns = send_ptr[R], nr = recv_ptr[R];
     if (recvback_ptr[R] != ns) return fail(c, JX_EINVAL, "recvback lists must mirror the send lists");

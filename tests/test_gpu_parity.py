@@ -451,6 +451,33 @@ def test_kernel_variant_requires_its_record_layout_before_upload():
         p.close()
 
 
+def test_restart_file_continues_bit_exactly(tmp_path):
+    """write_hdf5 / read_hdf5 (the reference's restart format, jexpresso_b200/io_hdf5.py): 4 CK2N54 steps in one go and
+    2 steps -> restart files -> fresh context -> 2 steps give the same bits (deterministic DSS)."""
+    from jexpresso_b200 import io_hdf5
+    spec = box3d((4, 3, 3), 4, warp=0.05)
+    sems, qns, qes, us = euler_case(spec, 1, lpert=True)
+    inputs = _inputs(True, True, 3)
+    N, neqs = sems[0].mesh.npoin, 5
+
+    def advance(u0, qe, nsteps):
+        p = jrhs.params_setup(sems[0], qe, inputs, pow_mode=1, dss_mode=0)
+        try:
+            u = u0.copy()
+            return u, jrhs.time_loop_bang(inputs, p, u, nsteps)
+        finally:
+            p.close()
+
+    u4, t4 = advance(us[0], qes[0], 4)
+    u2, t2 = advance(us[0], qes[0], 2)
+    io_hdf5.write_hdf5(N, u2, qes[0], t2, str(tmp_path), nvar=neqs)
+    q, qe, t = io_hdf5.read_hdf5(str(tmp_path), N, neqs)
+    assert t == t2
+    qe[:, neqs] = qes[0][:, neqs]                       # the pressure column of qe is not part of the reference's restart files
+    ur, _ = advance(np.ascontiguousarray(q[:, :neqs].reshape(-1, order="F")), qe, 2)
+    assert np.array_equal(ur, u4)
+
+
 def test_shared_reciprocal_division():
     """The two-stage flux functors divide several momenta by one density with a shared refined reciprocal
     (jx_functors.cuh Recip); it must be bit-identical to the correctly rounded `/` the oracle uses."""
