@@ -45,6 +45,8 @@ typedef struct jx_ctx jx_ctx;
 #define JX_EQ_EULER_ENERGY 1   /* problems/CompEuler/kelvinHelmholtzChan2022 (2D) */
 #define JX_EQ_ADVDIFF 2        /* problems/AdvDiff/kopriva (2D), problems/AdvDiff/3d_periodic */
 #define JX_EQ_SHALLOW_WATER 3  /* problems/ShallowWater/SoliWaveIsland (2D) */
+#define JX_EQ_EULER_THETA_LES 4 /* problems/CompEuler/LESICP1 (3D, TOTAL): theta-form fluxes, sponge + Coriolis + geostrophic source;
+                                  phys[8..12] = lsponge, zsponge, zmax, f, alpha */
 
 /* stage drivers (OrdinaryDiffEq algorithms used at src/kernel/solvers/TimeIntegrators.jl:597-607) */
 #define JX_SCHEME_CK2N54 0

@@ -13,6 +13,7 @@ EQ_EULER_THETA = 0      # CompEuler θ-form (problems/CompEuler/3d, problems/Com
 EQ_EULER_ENERGY = 1     # CompEuler total energy (problems/CompEuler/kelvinHelmholtzChan2022)
 EQ_ADVDIFF = 2          # AdvDiff (problems/AdvDiff/kopriva, 3d_periodic)
 EQ_SHALLOW_WATER = 3    # ShallowWater (problems/ShallowWater/SoliWaveIsland)
+EQ_EULER_THETA_LES = 4  # CompEuler θ-form with the sponge / Coriolis / geostrophic source of problems/CompEuler/LESICP1
 
 SCHEME_CK2N54 = 0       # CarpenterKennedy2N54
 SCHEME_SSPRK54 = 1
@@ -60,4 +61,12 @@ def advdiff_packed(u=0.5, v=1.0, w=0.0):
     """Packed constants of the AdvDiff functor: the constant wind of problems/AdvDiff/*/user_flux.jl in phys[8..10]."""
     ph = [0.0] * 16
     ph[8], ph[9], ph[10] = u, v, w
+    return ph
+
+
+def les_packed(zmax, lsponge=True, zsponge=0.0, f=1.0e-4, alpha=0.5, base=None):
+    """Packed constants of the LESICP1 functor (problems/CompEuler/LESICP1/user_source.jl:30-103): PhysicalConst in [0..7],
+    [8] = inputs[:lsponge], [9] = inputs[:zsponge], [10] = zmax of the mesh, [11] = Coriolis parameter, [12] = sponge alpha."""
+    ph = list((base or PhysicalConst()).packed()) + [0.0] * 8
+    ph[8], ph[9], ph[10], ph[11], ph[12] = (1.0 if lsponge else 0.0), float(zsponge), float(zmax), float(f), float(alpha)
     return ph

@@ -23,7 +23,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import capi
-from .physics import (BC_FREE_SLIP, BC_SKIP, EQ_ADVDIFF, EQ_EULER_ENERGY, EQ_EULER_THETA, EQ_SHALLOW_WATER,
+from .physics import (BC_FREE_SLIP, BC_SKIP, EQ_ADVDIFF, EQ_EULER_ENERGY, EQ_EULER_THETA, EQ_EULER_THETA_LES, EQ_SHALLOW_WATER,
                       SCHEME_CK2N54, SCHEME_SSPRK33, SCHEME_SSPRK54, PhysicalConst)
 
 __all__ = ["Params", "params_setup", "rhs_bang", "time_loop_bang", "face_kinds", "float32_dt"]
@@ -31,7 +31,7 @@ __all__ = ["Params", "params_setup", "rhs_bang", "time_loop_bang", "face_kinds",
 _PERIODIC_TAGS = {"periodicx", "periodicy", "periodicz", "periodic1", "periodic2", "periodic3", "Laguerre"}
 _SCHEMES = {"CarpenterKennedy2N54": SCHEME_CK2N54, "SSPRK54": SCHEME_SSPRK54, "SSPRK33": SCHEME_SSPRK33}
 _EQS = {"CompEuler": EQ_EULER_THETA, "CompEulerEnergy": EQ_EULER_ENERGY, "AdvDiff": EQ_ADVDIFF,
-        "ShallowWater": EQ_SHALLOW_WATER}
+        "ShallowWater": EQ_SHALLOW_WATER, "CompEulerLES": EQ_EULER_THETA_LES}
 
 
 def face_kinds(tags):
@@ -63,7 +63,7 @@ def params_setup(sem, qe, inputs, *, device=0, rank=0, nranks=1, nccl_uid=None, 
     interface lists) to its GPU and return the ``params`` handle ``rhs_bang`` takes."""
     m = sem.mesh
     eq_id = _EQS[eqs] if isinstance(eqs, str) else int(eqs)
-    neqs = {EQ_EULER_THETA: m.nsd + 2, EQ_EULER_ENERGY: 4, EQ_ADVDIFF: 1, EQ_SHALLOW_WATER: 3}[eq_id]
+    neqs = {EQ_EULER_THETA: m.nsd + 2, EQ_EULER_ENERGY: 4, EQ_ADVDIFF: 1, EQ_SHALLOW_WATER: 3, EQ_EULER_THETA_LES: 5}[eq_id]
     lpert = inputs.get("SOL_VARS_TYPE", "TOTAL") == "PERT"
     lvisc = bool(inputs.get("lvisc", False))
     mu = np.zeros(neqs)

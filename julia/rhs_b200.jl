@@ -34,11 +34,14 @@ end
 """
 Equation-set id of include/jexrhs.h.  The reference names the equation directory in `inputs[:_parsed_equations]`
 (run.jl:167); the total-energy form is CompEuler with `inputs[:energy_equation] == "energy"` (mod_inputs.jl:1027-1028,
-run.jl:305-314).
+run.jl:305-314); the LESICP1 case has a source hook of its own (sponge, Coriolis, geostrophic wind).
 """
 function equation_id(inputs)
     eqs = inputs[:_parsed_equations]
-    eqs == "CompEuler"    && return inputs[:energy_equation] == "theta" ? 0 : 1
+    if eqs == "CompEuler"
+        inputs[:_parsed_case_name] == "LESICP1" && return 4          # theta fluxes + sponge / Coriolis / geostrophic source
+        return inputs[:energy_equation] == "theta" ? 0 : 1
+    end
     eqs == "AdvDiff"      && return 2
     eqs == "ShallowWater" && return 3
     error("libjexrhs has no device functor registered for problems/$eqs")
@@ -51,10 +54,16 @@ user_source.jl, not inputs): slots 8-10 the AdvDiff wind; slots 9-15 the Shallow
 (jexpresso_b200/physics.py: advdiff_packed, swe_packed).  `inputs[:b200_case_constants]` (a Vector{Float64} for slots
 8-15) overrides the table below for cases it does not list.
 """
-function packed_constants(inputs)
+function packed_constants(inputs, mesh)
     PC = J.PHYS_CONST
     phys = zeros(Float64, 16)
     phys[1:8] .= (PC.C0, PC.γ, PC.g, PC.Rair, PC.cp, PC.cv, PC.pref, PC.γm1)
+    if inputs[:_parsed_equations] == "CompEuler" && inputs[:_parsed_case_name] == "LESICP1"
+        # problems/CompEuler/LESICP1/user_source.jl:30-103: sponge switch and base height from the deck, zmax from the mesh,
+        # f = 1.0e-4 and alpha = 0.5 are literals of the hook
+        phys[9:13] .= (inputs[:lsponge] ? 1.0 : 0.0, inputs[:zsponge], mesh.zmax, 1.0e-4, 0.5)
+        return phys
+    end
     if haskey(inputs, :b200_case_constants)
         phys[9:16] .= inputs[:b200_case_constants]
     else
@@ -85,7 +94,7 @@ function b200_setup(params, inputs; device = 0, rank = 0, nranks = 1, uid = C_NU
     c = ctx[]
     mesh, metrics, basis = params.mesh, params.metrics, params.basis
     nsd = mesh.nsd; ngl = mesh.ngl; neqs = params.neqs
-    phys = packed_constants(inputs)
+    phys = packed_constants(inputs, mesh)
     # engine options (include/jexrhs.h): inputs[:b200_dss] = :gather (deterministic, reference summation order, default)
     # or :atomics (throughput mode); the element kernel is chosen by the library (JX_ELEM_AUTO) unless
     # inputs[:b200_elem_kernel] names a variant; the shared jx_pow keeps the equation of state reproducible

@@ -43,6 +43,8 @@
 #define JXO_EQ_EULER_ENERGY 1
 #define JXO_EQ_ADVDIFF 2
 #define JXO_EQ_SHALLOW_WATER 3
+#define JXO_EQ_EULER_THETA_LES 4   /* problems/CompEuler/LESICP1: theta-form fluxes, sponge + Coriolis + geostrophic source */
+#define JXO_IS_THETA(P) ((P)->eq_id == JXO_EQ_EULER_THETA || (P)->eq_id == JXO_EQ_EULER_THETA_LES)
 
 #define BC_SENTINEL 4325789.0
 
@@ -91,7 +93,7 @@ static inline double perfectGasLaw_rtheta2P(const jxo_problem *P, double rho, do
 
 /* problems/CompEuler/3d/user_flux.jl:1-77 (TOTAL :1-37, PERT :39-77) */
 static void user_flux_3d(const jxo_problem *P, double *F, double *G, double *H, const double *q, const double *qe) {
-    if (P->eq_id == JXO_EQ_EULER_THETA) {
+    if (JXO_IS_THETA(P)) {      /* LESICP1/user_flux.jl:1-40 is the TOTAL branch of 3d/user_flux.jl, term by term */
         if (!P->lpert) {
             double r = q[0], ru = q[1], rv = q[2], rw = q[3], rt = q[4];
             double th = rt / r, u = ru / r, v = rv / r, w = rw / r;
@@ -167,6 +169,30 @@ static void user_source(const jxo_problem *P, double *S, const double *q, const 
     if (P->eq_id == JXO_EQ_EULER_THETA) {
         double r = q[0];
         S[P->nsd] = -r * P->phys[2];
+    } else if (P->eq_id == JXO_EQ_EULER_THETA_LES) {
+        /* problems/CompEuler/LESICP1/user_source.jl:1-103 (TOTAL): gravity; top sponge relaxing the momenta towards qe
+         * (inputs[:lsponge] = phys[8], inputs[:zsponge] = phys[9], zmax = phys[10], alpha = phys[12] = 0.5); Coriolis with
+         * f = phys[11] = 1.0e-4 and the geostrophic wind of the reference state.  sinpi: Julia's; here sin(pi*x). */
+        const double f = P->phys[11];
+        S[3] = -q[0] * P->phys[2];
+        if (P->phys[8] != 0.0) {
+            const double zs = P->phys[9], zmax = P->phys[10], z = xyz[2];
+            double betay_coe = 0.0;
+            if (z >= zs) betay_coe = P->phys[12] * sin(3.14159265358979323846 * (0.5 * (z - zs) / (zmax - zs)));
+            const double ctop = 1.0 * betay_coe;
+            const double cs = 1.0 - (1.0 - ctop) * (1.0 - 0.0) * (1.0 - 0.0) * (1.0 - 0.0) * (1.0 - 0.0);
+            S[1] -= cs * (q[1] - qe[1]);
+            S[2] -= cs * (q[2] - qe[2]);
+            S[3] -= cs * (q[3] - qe[3]);
+        }
+        {
+            const double u_vel = q[1], v_vel = q[2];
+            S[1] += f * v_vel;
+            S[2] -= f * u_vel;
+            const double U_geo = qe[1] / qe[0], V_geo = qe[2] / qe[0];
+            S[1] -= q[0] * f * V_geo;
+            S[2] += q[0] * f * U_geo;
+        }
     } else if (P->eq_id == JXO_EQ_SHALLOW_WATER) {
         /* problems/ShallowWater/SoliWaveIsland/user_source.jl:34-73: -g (H - He) grad(Hb) over the conical island
          * (phys[9] = cone height, [13],[14] = centre, [15] = radius) and the dry-node momentum relaxation (phys[10]) */
@@ -189,7 +215,7 @@ static void user_source(const jxo_problem *P, double *S, const double *q, const 
 /* problems/CompEuler/3d/user_primitives.jl:1-15, problems/CompEuler/theta/user_primitives.jl:1-13 */
 static void user_primitives(const jxo_problem *P, const double *u, const double *qe, double *up) {
     int q = P->neqs;
-    if (P->eq_id == JXO_EQ_EULER_THETA) {
+    if (JXO_IS_THETA(P)) {
         if (!P->lpert) {
             up[0] = u[0];
             for (int e = 1; e < q; ++e) up[e] = u[e] / u[0];

@@ -109,3 +109,40 @@ def test_advdiff_kopriva_golden_end_state_on_gpu():
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "AdvDiff_kopriva.npz"))
     worst = float(np.max(np.abs(np.sort(u) - np.sort(g["q1"]))))
     assert worst < 1e-9, worst
+
+
+@pytest.mark.parametrize("lvisc", [False, True])
+def test_les_source_functor_one_rhs(lvisc):
+    """problems/CompEuler/LESICP1 (first part): theta-form fluxes with the sponge + Coriolis + geostrophic source
+    (three source components, node coordinates, reference state) on the generic kernel.  Without the sponge every operation is
+    IEEE-exact on both sides: bit-identical to the oracle; with it the one sinpi differs by <= 2 ulp between CUDA and libm."""
+    from jexpresso_b200.physics import EQ_EULER_THETA_LES, les_packed
+    from helpers import MU3, euler_case
+    spec = box3d((4, 3, 5), 4, warp=0.05)
+    sems, qns, qes, us = euler_case(spec, 1, lpert=False)
+    qes[0][:, 1] = 10.0 * qes[0][:, 0]
+    qes[0][:, 2] = 2.0 * qes[0][:, 0]
+    zmax = float(sems[0].mesh.z.max())
+    N = sems[0].mesh.npoin
+    for lsponge in (False, True):
+        ph = les_packed(zmax, lsponge=lsponge, zsponge=6000.0)
+        prob = ref.RefProblem(sems[0], qes[0], eq_id=EQ_EULER_THETA_LES, lpert=False, lsource=True, lvisc=lvisc, visc_coeff=MU3,
+                              phys=ph, pow_mode=1, neqs=5)
+        run = ref.RefRun([prob])
+        uo, duo = [us[0].copy()], [np.zeros_like(us[0])]
+        run.rhs(duo, uo, 0.0)
+        inputs = {"SOL_VARS_TYPE": "TOTAL", "lsource": True, "lvisc": lvisc, "mu": MU3, "dt": 0.1, "ode_solver": "CarpenterKennedy2N54"}
+        for dss in (0, 1):
+            p = jrhs.params_setup(sems[0], qes[0], inputs, eqs="CompEulerLES", phys=ph, pow_mode=1, dss_mode=dss)
+            try:
+                assert p.ctx.kernel_variant() == 0
+                u, du = us[0].copy(), np.empty_like(us[0])
+                jrhs.rhs_bang(du, u, p, 0.0)
+            finally:
+                p.close()
+            assert np.array_equal(u, uo[0])
+            if dss == 0 and not lsponge:
+                assert np.array_equal(du, duo[0]), rel_err_per_node(du, duo[0])
+            for e in range(5):
+                pn, l2 = rel_err_per_node(du[e * N:(e + 1) * N], duo[0][e * N:(e + 1) * N])
+                assert pn <= 1e-12 and l2 <= 1e-10, (lsponge, dss, e, pn, l2)
