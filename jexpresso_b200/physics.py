@@ -30,6 +30,13 @@ class PhysicalConst:
     cv: float = 718.0
     pref: float = 101200.0
     g: float = 9.80616
+    # SGS closures (globalConstantsPhysics.jl:15-31; read by allocate_SGS, sgsStructs.jl:77-120)
+    mu_mol: float = 1.8e-5
+    kappa_mol: float = 2.4e-5
+    Sc_t: float = 0.7
+    Pr_t: float = 0.7
+    Ri_crit: float = 0.25
+    C_s: float = 0.21
 
     @property
     def gamma(self):
@@ -46,6 +53,14 @@ class PhysicalConst:
     def packed(self):
         """Packed array handed to jx_set_problem: [C0, γ, g, Rair, cp, cv, pref, γ-1]."""
         return [self.C0, self.gamma, self.g, self.Rair, self.cp, self.cv, self.pref, self.gamma - 1.0]
+
+
+    def sgs_packed(self):
+        """Constants handed to jx_set_sgs: [Pr_t, Sc_t, mu_mol, kappa_mol, Ri_crit, C_s]."""
+        return [self.Pr_t, self.Sc_t, self.mu_mol, self.kappa_mol, self.Ri_crit, self.C_s]
+
+
+VISC_AV, VISC_SMAG, VISC_VREM = 0, 1, 2     # inputs[:visc_model] = AV() | SMAG() | VREM()  (jx_set_sgs)
 
 
 def swe_packed(g=9.81, h_wet=1.0e-3, cone_height=0.93, sigma_dry=25.0, cone_xc=12.5, cone_yc=0.0, cone_rc=3.6):

@@ -30,7 +30,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-__all__ = ["Mesh", "BoxSpec", "structured_box", "compute_xy_partition", "part_subbox"]
+__all__ = ["Mesh", "BoxSpec", "structured_box", "compute_xy_partition", "part_subbox", "element_sizes", "effective_delta_l"]
 
 
 @dataclass
@@ -388,3 +388,27 @@ def _box2d(spec, xi, sub, rank, nranks):
                 ip2gip=ip2gip, gip2owner=np.full(ltotal, rank, np.int64), el2gel=el2gel,
                 xmin=float(spec.lo[0]), xmax=float(spec.hi[0]), ymin=float(spec.lo[1]), ymax=float(spec.hi[1]),
                 zmin=0.0, zmax=0.0, rank=rank, nranks=nranks, spec=spec, sub=sub)
+
+
+def element_sizes(mesh):
+    """compute_element_size! (mesh.jl:5646-5711): per element, the extent of the bounding box of its corner nodes, shortest
+    direction ("as if it were linear")."""
+    n = mesh.ngl
+    c = np.asarray(mesh.connijk) - 1
+    ends = [0, n - 1]
+    if mesh.nsd == 3:
+        corners = np.stack([c[:, i, j, k] for i in ends for j in ends for k in ends], axis=1)
+        axes = (mesh.x, mesh.y, mesh.z)
+    else:
+        c = c.reshape(mesh.nelem, n, n)
+        corners = np.stack([c[:, i, j] for i in ends for j in ends], axis=1)
+        axes = (mesh.x, mesh.y)
+    ext = [a[corners].max(axis=1) - a[corners].min(axis=1) for a in axes]
+    return np.minimum.reduce(ext)
+
+
+def effective_delta_l(meshes):
+    """mesh.Δeffective_l = max over ALL ranks of Δelem, divided by nop (compute_element_size_driver, mesh.jl:5621-5632: the
+    MPI.Allreduce(MAX) is the max over the list here)."""
+    meshes = list(meshes) if isinstance(meshes, (list, tuple)) else [meshes]
+    return float(max(element_sizes(m).max() for m in meshes) / meshes[0].nop)

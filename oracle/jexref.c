@@ -66,6 +66,14 @@ typedef struct {
     const double *nx, *ny, *nz;      /* same shape */
     const int32_t *face_kind;        /* 0: periodic tag (skipped, BCs.jl:621-623); 1: free-slip hook */
     double xmin, xmax, ymin, ymax, zmin, zmax;
+    /* SGS viscosity: the SGS_SMAG / SGS_VREM structs of sgsStructs.jl:6-72 as allocate_SGS fills them
+     * (:77-120) plus the two flags of params_setup.jl:249-253.  visc_model 0 = AV (sgs === nothing) */
+    int32_t visc_model;       /* 0: AV; 1: SMAG(); 2: VREM()  (inputs[:visc_model]) */
+    int32_t lrichardson;      /* inputs[:lrichardson], default true for SMAG/VREM */
+    int32_t ltheta_eqn;       /* !(inputs[:energy_equation] == "energy") */
+    int32_t sgs_pad;
+    double sgs[8];            /* Pr_t, Sc_t, mu_mol, kappa_mol, Ri_crit, C_s of PhysicalConst; [6] = mesh.Δeffective_l (mesh.jl:5632) */
+    const int64_t *ad_lvl;    /* mesh.ad_lvl [nelem] (calculate_effective_delta, mesh.jl:5749-5751) or NULL = all zero */
 } jxo_problem;
 
 static inline double eos_pow(const jxo_problem *P, double base, double expo) {
@@ -283,6 +291,7 @@ typedef struct {
     double *rhs_diff_xi, *rhs_diff_eta, *rhs_diff_zeta, *rhs_diff_el;
     double *RHS_visc;  /* [npoin, neqs] */
     double *F, *G, *H, *S, *uprim; /* [n^d, neqs(+1)] */
+    double *mu_turb;   /* sgs.μ_turb [npoin]: per-node cache, overwritten element by element (SGS.jl:1257, 1405) */
 } jxo_work;
 
 size_t jxo_work_doubles(const jxo_problem *P) {
@@ -291,6 +300,7 @@ size_t jxo_work_doubles(const jxo_problem *P) {
     size_t tot = (size_t)P->npoin * (P->neqs + 1) + el;
     if (P->lvisc) tot += 4 * el + (size_t)P->npoin * P->neqs;
     tot += 4 * nd * P->neqs + nd * (P->neqs + 1);
+    if (P->lvisc && P->visc_model) tot += (size_t)P->npoin;
     return tot;
 }
 
@@ -310,7 +320,8 @@ static void carve(const jxo_problem *P, double *mem, jxo_work *W) {
     W->G = mem; mem += nd * P->neqs;
     W->H = mem; mem += nd * P->neqs;
     W->S = mem; mem += nd * P->neqs;
-    W->uprim = mem;
+    W->uprim = mem; mem += nd * (P->neqs + 1);
+    W->mu_turb = (P->lvisc && P->visc_model) ? mem : NULL;
 }
 
 /* rhs.jl:29-47 u2uaux! / uaux2u! */
@@ -592,6 +603,374 @@ static void viscous_rhs_el_2d(const jxo_problem *P, jxo_work *W) {
     for (size_t t = 0; t < tot; ++t) W->rhs_diff_el[t] = W->rhs_diff_xi[t] + W->rhs_diff_eta[t];
 }
 
+/* ------------------------------------------------------------------------------------------
+ * SGS viscosity: Smagorinsky and Vreman.  PARITY UNPINNED: the reference holds no golden vector of a
+ * SMAG()/VREM() deck; restated term by term from SGS.jl and rhs.jl and cross-checked against an independent numpy
+ * transcription (tests/test_sgs_cpu.py).  Dry path only: micro = size(mp.Tabs, 1) == 1 (no microphysics).
+ * Rounding contract: compute_sgs_cache! is plain Julia (no @turbo): every `a += b*c` is a multiply and an add, separately
+ * rounded; the cache-reading _expansion_visc! runs its ii-loops under @turbo: sequential FMA chains, as everywhere else.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int lrichardson, ltheta_eqn, vrem;
+    double Pr_t, Sc_t, mu_mol, kappa_mol, Ri_crit, C_s2, C_vrem, g;
+} sgs_consts;
+
+/* allocate_SGS, sgsStructs.jl:77-120: C_s2 = T(C_s * C_s), C_vrem = T(2.5 * C_s * C_s) */
+static sgs_consts sgs_setup(const jxo_problem *P) {
+    sgs_consts c;
+    c.lrichardson = P->lrichardson; c.ltheta_eqn = P->ltheta_eqn; c.vrem = (P->visc_model == 2);
+    c.Pr_t = P->sgs[0]; c.Sc_t = P->sgs[1]; c.mu_mol = P->sgs[2]; c.kappa_mol = P->sgs[3]; c.Ri_crit = P->sgs[4];
+    c.C_s2 = P->sgs[5] * P->sgs[5];
+    c.C_vrem = 2.5 * P->sgs[5] * P->sgs[5];
+    c.g = P->phys[2];
+    return c;
+}
+
+/* Richardson stability function, SGS.jl:1241-1253 (= :1382-1399, :1519-1530, :1637-1649) */
+static double sgs_f_Ri(const sgs_consts *c, double N2_val, double Sij2_val) {
+    double Ri = Sij2_val > 1e-12 ? N2_val / Sij2_val : 0.0;
+    if (Ri >= c->Ri_crit) return 0.0;
+    if (Ri >= 0.0) {
+        double ratio = Ri / c->Ri_crit;
+        return (1.0 - ratio) * (1.0 - ratio);
+    }
+    return fmin(sqrt(1.0 - 16.0 * Ri), 3.0);
+}
+
+/* SGS.jl:1118-1260 compute_sgs_cache!(::SGS_SMAG, ..., ::NSD_3D) and :1262-1408 (::SGS_VREM): one pass over the nodes of
+ * element iel, fills sgs.μ_turb[ip] */
+static void compute_sgs_cache_3d(const jxo_problem *P, jxo_work *W, const sgs_consts *c, int64_t iel, double D2) {
+    const int n = P->ngl;
+    const int64_t E = P->nelem;
+    const int64_t *conn = P->connijk;
+    const double *dpsi = P->dpsi;
+    const double *U = W->uprim;
+    for (int m = 0; m < n; ++m) for (int l = 0; l < n; ++l) for (int k = 0; k < n; ++k) {
+        int64_t ip = CONN3(iel, k, l, m) - 1;
+        double dudxi = 0, dudeta = 0, dudzeta = 0, dvdxi = 0, dvdeta = 0, dvdzeta = 0, dwdxi = 0, dwdeta = 0, dwdzeta = 0;
+        double dtdxi = 0, dtdeta = 0, dtdzeta = 0;
+        for (int ii = 0; ii < n; ++ii) {
+            dudxi = dudxi + DPSI(ii, k) * LOC4(U, ii, l, m, 1);
+            dudeta = dudeta + DPSI(ii, l) * LOC4(U, k, ii, m, 1);
+            dudzeta = dudzeta + DPSI(ii, m) * LOC4(U, k, l, ii, 1);
+            dvdxi = dvdxi + DPSI(ii, k) * LOC4(U, ii, l, m, 2);
+            dvdeta = dvdeta + DPSI(ii, l) * LOC4(U, k, ii, m, 2);
+            dvdzeta = dvdzeta + DPSI(ii, m) * LOC4(U, k, l, ii, 2);
+            dwdxi = dwdxi + DPSI(ii, k) * LOC4(U, ii, l, m, 3);
+            dwdeta = dwdeta + DPSI(ii, l) * LOC4(U, k, ii, m, 3);
+            dwdzeta = dwdzeta + DPSI(ii, m) * LOC4(U, k, l, ii, 3);
+            dtdxi = dtdxi + DPSI(ii, k) * LOC4(U, ii, l, m, 4);
+            dtdeta = dtdeta + DPSI(ii, l) * LOC4(U, k, ii, m, 4);
+            dtdzeta = dtdzeta + DPSI(ii, m) * LOC4(U, k, l, ii, 4);
+        }
+        double xix = MET3(P->met[0], iel, k, l, m), xiy = MET3(P->met[1], iel, k, l, m), xiz = MET3(P->met[2], iel, k, l, m);
+        double etx = MET3(P->met[3], iel, k, l, m), ety = MET3(P->met[4], iel, k, l, m), etz = MET3(P->met[5], iel, k, l, m);
+        double zex = MET3(P->met[6], iel, k, l, m), zey = MET3(P->met[7], iel, k, l, m), zez = MET3(P->met[8], iel, k, l, m);
+        double dudx = dudxi * xix + dudeta * etx + dudzeta * zex;
+        double dudy = dudxi * xiy + dudeta * ety + dudzeta * zey;
+        double dudz = dudxi * xiz + dudeta * etz + dudzeta * zez;
+        double dvdx = dvdxi * xix + dvdeta * etx + dvdzeta * zex;
+        double dvdy = dvdxi * xiy + dvdeta * ety + dvdzeta * zey;
+        double dvdz = dvdxi * xiz + dvdeta * etz + dvdzeta * zez;
+        double dwdx = dwdxi * xix + dwdeta * etx + dwdzeta * zex;
+        double dwdy = dwdxi * xiy + dwdeta * ety + dwdzeta * zey;
+        double dwdz = dwdxi * xiz + dwdeta * etz + dwdzeta * zez;
+        /* Sij (SMAG :1189-1198; VREM recomputes it for the Richardson number only, :1384-1389) */
+        double S11 = dudx, S22 = dvdy, S33 = dwdz;
+        double S12 = 0.5 * (dudy + dvdx), S13 = 0.5 * (dudz + dwdx), S23 = 0.5 * (dvdz + dwdy);
+        double S_ij_S_ij = S11 * S11 + S22 * S22 + S33 * S33 + 2.0 * (S12 * S12 + S13 * S13 + S23 * S23);
+        double Sij2_val = 2.0 * S_ij_S_ij;
+        /* N² dry, micro == 1 (:1203-1209) */
+        double N2_val = 0.0;
+        if (c->lrichardson) {
+            double th = LOC4(U, k, l, m, 4);
+            double dtdz = dtdxi * xiz + dtdeta * etz + dtdzeta * zez;
+            N2_val = fabs(th) > 1e-12 ? (c->g / th) * dtdz : 0.0;
+        }
+        double f_Ri_val = 1.0;
+        if (c->lrichardson) f_Ri_val = sgs_f_Ri(c, N2_val, Sij2_val);
+        double rho = LOC4(U, k, l, m, 0);
+        if (!c->vrem) {
+            double Sij_val = sqrt(Sij2_val);
+            W->mu_turb[ip] = rho * c->C_s2 * D2 * Sij_val * f_Ri_val;                        /* :1257 */
+        } else {
+            /* Vreman β tensor, full velocity gradient (:1334-1344) */
+            double b11 = D2 * (dudx * dudx + dudy * dudy + dudz * dudz);
+            double b12 = D2 * (dudx * dvdx + dudy * dvdy + dudz * dvdz);
+            double b13 = D2 * (dudx * dwdx + dudy * dwdy + dudz * dwdz);
+            double b22 = D2 * (dvdx * dvdx + dvdy * dvdy + dvdz * dvdz);
+            double b23 = D2 * (dvdx * dwdx + dvdy * dwdy + dvdz * dwdz);
+            double b33 = D2 * (dwdx * dwdx + dwdy * dwdy + dwdz * dwdz);
+            double B_b = b11 * b22 + b11 * b33 + b22 * b33 - (b12 * b12 + b13 * b13 + b23 * b23);
+            double u_ij_u_ij = dudx * dudx + dudy * dudy + dudz * dudz + dvdx * dvdx + dvdy * dvdy + dvdz * dvdz + dwdx * dwdx +
+                               dwdy * dwdy + dwdz * dwdz;
+            double mu_base = (u_ij_u_ij > 2.220446049250313e-16 && B_b > 0.0) ? rho * c->C_vrem * sqrt(B_b / u_ij_u_ij) : 0.0;
+            W->mu_turb[ip] = mu_base * f_Ri_val;                                             /* :1402-1405 */
+        }
+    }
+}
+
+/* SGS.jl:1416-1535 (SMAG) / :1537-1655 (VREM) compute_sgs_cache!(..., ::NSD_2D): y is the vertical */
+static void compute_sgs_cache_2d(const jxo_problem *P, jxo_work *W, const sgs_consts *c, int64_t iel, double D2) {
+    const int n = P->ngl;
+    const int64_t E = P->nelem;
+    const int64_t *conn = P->connijk;
+    const double *dpsi = P->dpsi;
+    const double *U = W->uprim;
+    for (int l = 0; l < n; ++l) for (int k = 0; k < n; ++k) {
+        int64_t ip = CONN2(iel, k, l) - 1;
+        double dudxi = 0, dudeta = 0, dvdxi = 0, dvdeta = 0, dtdxi = 0, dtdeta = 0;
+        for (int ii = 0; ii < n; ++ii) {
+            dudxi = dudxi + DPSI(ii, k) * LOC3(U, ii, l, 1);
+            dudeta = dudeta + DPSI(ii, l) * LOC3(U, k, ii, 1);
+            dvdxi = dvdxi + DPSI(ii, k) * LOC3(U, ii, l, 2);
+            dvdeta = dvdeta + DPSI(ii, l) * LOC3(U, k, ii, 2);
+            dtdxi = dtdxi + DPSI(ii, k) * LOC3(U, ii, l, 3);
+            dtdeta = dtdeta + DPSI(ii, l) * LOC3(U, k, ii, 3);
+        }
+        double xix = MET2(P->met[0], iel, k, l), xiy = MET2(P->met[1], iel, k, l);
+        double etx = MET2(P->met[2], iel, k, l), ety = MET2(P->met[3], iel, k, l);
+        double dudx = dudxi * xix + dudeta * etx, dudy = dudxi * xiy + dudeta * ety;
+        double dvdx = dvdxi * xix + dvdeta * etx, dvdy = dvdxi * xiy + dvdeta * ety;
+        double N2_val = 0.0;
+        if (c->lrichardson) {
+            double th = LOC3(U, k, l, 3);
+            double dtdy = dtdxi * xiy + dtdeta * ety;
+            N2_val = fabs(th) > 1e-12 ? (c->g / th) * dtdy : 0.0;
+        }
+        double rho = LOC3(U, k, l, 0);
+        if (!c->vrem) {
+            double S11 = dudx, S22 = dvdy, S12 = 0.5 * (dudy + dvdx);
+            double S_ij_S_ij = S11 * S11 + S22 * S22 + 2.0 * S12 * S12;                      /* :1474 */
+            double Sij2_val = 2.0 * S_ij_S_ij;
+            double Sij_val = sqrt(Sij2_val);
+            double f_Ri_val = 1.0;
+            if (c->lrichardson) f_Ri_val = sgs_f_Ri(c, N2_val, Sij2_val);
+            W->mu_turb[ip] = rho * c->C_s2 * D2 * Sij_val * f_Ri_val;
+        } else {
+            double b11 = D2 * (dudx * dudx + dudy * dudy);
+            double b12 = D2 * (dudx * dvdx + dudy * dvdy);
+            double b22 = D2 * (dvdx * dvdx + dvdy * dvdy);
+            double B_b = b11 * b22 - b12 * b12;
+            double u_ij_u_ij = dudx * dudx + dudy * dudy + dvdx * dvdx + dvdy * dvdy;
+            double f_Ri_val = 1.0;
+            if (c->lrichardson) {
+                double hs = 0.5 * (dudy + dvdx);
+                double Sij2_val = 2.0 * (dudx * dudx + dvdy * dvdy + 2.0 * (hs * hs));      /* :1638 */
+                f_Ri_val = sgs_f_Ri(c, N2_val, Sij2_val);
+            }
+            double mu_base = (u_ij_u_ij > 2.220446049250313e-16 && B_b > 0.0) ? rho * c->C_vrem * sqrt(B_b / u_ij_u_ij) : 0.0;
+            W->mu_turb[ip] = mu_base * f_Ri_val;
+        }
+    }
+}
+
+/* SGS.jl:1087-1109 (3D) / :1663-1685 (2D) cache-reading SGS_diffusion; ieq 0-based here, itemp = the temperature equation */
+static double SGS_diffusion(const jxo_problem *P, const sgs_consts *c, int ieq, int itemp, double rho, double mu_turb) {
+    if (ieq >= 1 && ieq < itemp) return (c->mu_mol + mu_turb) * P->visc_coeff[ieq];
+    if (ieq == itemp) {
+        double k_turb = mu_turb / (rho * c->Pr_t);
+        if (c->ltheta_eqn) return k_turb * P->visc_coeff[ieq];
+        return (c->kappa_mol + k_turb) * P->visc_coeff[ieq];
+    }
+    double k_turb_scalar = mu_turb / (rho * c->Sc_t);
+    return (c->kappa_mol + k_turb_scalar) * P->visc_coeff[ieq];
+}
+
+/* rhs.jl:1398-1461 _viscous_rhs_el_3d! with sgs isa AbstractSGSModel + rhs.jl:2582-2785 cache-reading _expansion_visc! (3D) */
+static void viscous_rhs_el_3d_sgs(const jxo_problem *P, jxo_work *W) {
+    const int n = P->ngl, q = P->neqs;
+    const int64_t E = P->nelem, N = P->npoin;
+    const int64_t *conn = P->connijk;
+    const double *dpsi = P->dpsi, *om = P->omega;
+    double *U = W->uprim;
+    double ql[16], qel[16], up[16];
+    const sgs_consts c = sgs_setup(P);
+    const double Delta = P->sgs[6];
+    for (int64_t iel = 0; iel < E; ++iel) {
+        double D_eff = P->ad_lvl ? ldexp(Delta, -(int)P->ad_lvl[iel]) : Delta;     /* rhs.jl:1416, mesh.jl:5749-5751 */
+        for (int k = 0; k < n; ++k) for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            int64_t ip = CONN3(iel, i, j, k) - 1;
+            for (int e = 0; e < q; ++e) ql[e] = W->uaux[ip + N * e];
+            for (int e = 0; e <= q; ++e) qel[e] = P->qe[ip + N * e];
+            user_primitives(P, ql, qel, up);
+            for (int e = 0; e < q; ++e) LOC4(U, i, j, k, e) = up[e];
+        }
+        compute_sgs_cache_3d(P, W, &c, iel, D_eff * D_eff);                         /* rhs.jl:1426-1434: Δ_effective^2 */
+        for (int ieq = 0; ieq < q; ++ieq) {
+            for (int m = 0; m < n; ++m) for (int l = 0; l < n; ++l) {
+                double wlm = om[l] * om[m];
+                for (int k = 0; k < n; ++k) {
+                    int64_t ip = CONN3(iel, k, l, m) - 1;
+                    double Je = MET3(P->met[9], iel, k, l, m);
+                    double wJ = om[k] * wlm * Je;
+                    double dudxi = 0, dudeta = 0, dudzeta = 0, dvdxi = 0, dvdeta = 0, dvdzeta = 0, dwdxi = 0, dwdeta = 0, dwdzeta = 0;
+                    for (int ii = 0; ii < n; ++ii) {
+                        dudxi = fma(DPSI(ii, k), LOC4(U, ii, l, m, 1), dudxi);
+                        dudeta = fma(DPSI(ii, l), LOC4(U, k, ii, m, 1), dudeta);
+                        dudzeta = fma(DPSI(ii, m), LOC4(U, k, l, ii, 1), dudzeta);
+                    }
+                    for (int ii = 0; ii < n; ++ii) {
+                        dvdxi = fma(DPSI(ii, k), LOC4(U, ii, l, m, 2), dvdxi);
+                        dvdeta = fma(DPSI(ii, l), LOC4(U, k, ii, m, 2), dvdeta);
+                        dvdzeta = fma(DPSI(ii, m), LOC4(U, k, l, ii, 2), dvdzeta);
+                    }
+                    for (int ii = 0; ii < n; ++ii) {
+                        dwdxi = fma(DPSI(ii, k), LOC4(U, ii, l, m, 3), dwdxi);
+                        dwdeta = fma(DPSI(ii, l), LOC4(U, k, ii, m, 3), dwdeta);
+                        dwdzeta = fma(DPSI(ii, m), LOC4(U, k, l, ii, 3), dwdzeta);
+                    }
+                    double xix = MET3(P->met[0], iel, k, l, m), xiy = MET3(P->met[1], iel, k, l, m), xiz = MET3(P->met[2], iel, k, l, m);
+                    double etx = MET3(P->met[3], iel, k, l, m), ety = MET3(P->met[4], iel, k, l, m), etz = MET3(P->met[5], iel, k, l, m);
+                    double zex = MET3(P->met[6], iel, k, l, m), zey = MET3(P->met[7], iel, k, l, m), zez = MET3(P->met[8], iel, k, l, m);
+                    double dudx = dudxi * xix + dudeta * etx + dudzeta * zex;
+                    double dudy = dudxi * xiy + dudeta * ety + dudzeta * zey;
+                    double dudz = dudxi * xiz + dudeta * etz + dudzeta * zez;
+                    double dvdx = dvdxi * xix + dvdeta * etx + dvdzeta * zex;
+                    double dvdy = dvdxi * xiy + dvdeta * ety + dvdzeta * zey;
+                    double dvdz = dvdxi * xiz + dvdeta * etz + dvdzeta * zez;
+                    double dwdx = dwdxi * xix + dwdeta * etx + dwdzeta * zex;
+                    double dwdy = dwdxi * xiy + dwdeta * ety + dwdzeta * zey;
+                    double dwdz = dwdxi * xiz + dwdeta * etz + dwdzeta * zez;
+                    double div_u = dudx + dvdy + dwdz;
+                    double rho = LOC4(U, k, l, m, 0);
+                    double mu_t = W->mu_turb[ip];
+                    double flux_x, flux_y, flux_z;
+                    if (ieq == 1) {
+                        double ev = SGS_diffusion(P, &c, ieq, 4, rho, mu_t);
+                        flux_x = 2.0 * ev * dudx - (2.0 / 3.0) * ev * div_u;
+                        flux_y = ev * (dudy + dvdx);
+                        flux_z = ev * (dudz + dwdx);
+                    } else if (ieq == 2) {
+                        double ev = SGS_diffusion(P, &c, ieq, 4, rho, mu_t);
+                        flux_x = ev * (dudy + dvdx);
+                        flux_y = 2.0 * ev * dvdy - (2.0 / 3.0) * ev * div_u;
+                        flux_z = ev * (dvdz + dwdy);
+                    } else if (ieq == 3) {
+                        double ev = SGS_diffusion(P, &c, ieq, 4, rho, mu_t);
+                        flux_x = ev * (dudz + dwdx);
+                        flux_y = ev * (dvdz + dwdy);
+                        flux_z = 2.0 * ev * dwdz - (2.0 / 3.0) * ev * div_u;
+                    } else {
+                        /* temperature (ieq == 4) and every other scalar (density, tracers): gradient of the variable itself; the
+                         * two branches of rhs.jl:2723-2763 differ only in the order of the SGS_diffusion call */
+                        double dsdxi = 0, dsdeta = 0, dsdzeta = 0;
+                        for (int ii = 0; ii < n; ++ii) {
+                            dsdxi = fma(DPSI(ii, k), LOC4(U, ii, l, m, ieq), dsdxi);
+                            dsdeta = fma(DPSI(ii, l), LOC4(U, k, ii, m, ieq), dsdeta);
+                            dsdzeta = fma(DPSI(ii, m), LOC4(U, k, l, ii, ieq), dsdzeta);
+                        }
+                        double dsdx = dsdxi * xix + dsdeta * etx + dsdzeta * zex;
+                        double dsdy = dsdxi * xiy + dsdeta * ety + dsdzeta * zey;
+                        double dsdz = dsdxi * xiz + dsdeta * etz + dsdzeta * zez;
+                        double ed = SGS_diffusion(P, &c, ieq, 4, rho, mu_t);
+                        flux_x = ed * dsdx;
+                        flux_y = ed * dsdy;
+                        flux_z = ed * dsdz;
+                    }
+                    const double sigma_mu = 1.0;                                             /* rhs.jl:2615 */
+                    double gxi = (xix * flux_x + xiy * flux_y + xiz * flux_z) * wJ * sigma_mu;
+                    double geta = (etx * flux_x + ety * flux_y + etz * flux_z) * wJ * sigma_mu;
+                    double gzeta = (zex * flux_x + zey * flux_y + zez * flux_z) * wJ * sigma_mu;
+                    for (int i = 0; i < n; ++i) {
+                        EL5(W->rhs_diff_xi, iel, i, l, m, ieq) = fma(-DPSI(i, k), gxi, EL5(W->rhs_diff_xi, iel, i, l, m, ieq));
+                        EL5(W->rhs_diff_eta, iel, k, i, m, ieq) = fma(-DPSI(i, l), geta, EL5(W->rhs_diff_eta, iel, k, i, m, ieq));
+                        EL5(W->rhs_diff_zeta, iel, k, l, i, ieq) = fma(-DPSI(i, m), gzeta, EL5(W->rhs_diff_zeta, iel, k, l, i, ieq));
+                    }
+                }
+            }
+        }
+    }
+    size_t tot = (size_t)E * n * n * n * q;
+    for (size_t t = 0; t < tot; ++t) W->rhs_diff_el[t] = W->rhs_diff_xi[t] + W->rhs_diff_eta[t] + W->rhs_diff_zeta[t];
+}
+
+/* rhs.jl:1255-1330 _viscous_rhs_el_2d! with sgs isa AbstractSGSModel + rhs.jl:2275-2400 cache-reading _expansion_visc! (2D);
+ * Δ^2 without the AMR level (rhs.jl:1282) */
+static void viscous_rhs_el_2d_sgs(const jxo_problem *P, jxo_work *W) {
+    const int n = P->ngl, q = P->neqs;
+    const int64_t E = P->nelem, N = P->npoin;
+    const int64_t *conn = P->connijk;
+    const double *dpsi = P->dpsi, *om = P->omega;
+    double *U = W->uprim;
+    double ql[16], qel[16], up[16];
+    const sgs_consts c = sgs_setup(P);
+    const double Delta = P->sgs[6];
+    for (int64_t iel = 0; iel < E; ++iel) {
+        for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) {
+            int64_t ip = CONN2(iel, i, j) - 1;
+            for (int e = 0; e < q; ++e) ql[e] = W->uaux[ip + N * e];
+            for (int e = 0; e <= q; ++e) qel[e] = P->qe[ip + N * e];
+            user_primitives(P, ql, qel, up);
+            for (int e = 0; e < q; ++e) LOC3(U, i, j, e) = up[e];
+        }
+        compute_sgs_cache_2d(P, W, &c, iel, Delta * Delta);
+        for (int ieq = 0; ieq < q; ++ieq) {
+            for (int l = 0; l < n; ++l) {
+                double wl = om[l];
+                for (int k = 0; k < n; ++k) {
+                    double Je = MET2(P->met[4], iel, k, l);
+                    double wJ = om[k] * wl * Je;
+                    int64_t ip = CONN2(iel, k, l) - 1;
+                    double rho = LOC3(U, k, l, 0);
+                    double mu_t = W->mu_turb[ip];
+                    double xix = MET2(P->met[0], iel, k, l), xiy = MET2(P->met[1], iel, k, l);
+                    double etx = MET2(P->met[2], iel, k, l), ety = MET2(P->met[3], iel, k, l);
+                    double dudxi = 0, dudeta = 0, dvdxi = 0, dvdeta = 0;
+                    for (int ii = 0; ii < n; ++ii) {
+                        dudxi = fma(DPSI(ii, k), LOC3(U, ii, l, 1), dudxi);
+                        dudeta = fma(DPSI(ii, l), LOC3(U, k, ii, 1), dudeta);
+                        dvdxi = fma(DPSI(ii, k), LOC3(U, ii, l, 2), dvdxi);
+                        dvdeta = fma(DPSI(ii, l), LOC3(U, k, ii, 2), dvdeta);
+                    }
+                    double dudx = dudxi * xix + dudeta * etx, dudy = dudxi * xiy + dudeta * ety;
+                    double dvdx = dvdxi * xix + dvdeta * etx, dvdy = dvdxi * xiy + dvdeta * ety;
+                    double div_u = dudx + dvdy;
+                    double flux_x, flux_y;
+                    if (ieq == 1) {
+                        double ev = SGS_diffusion(P, &c, ieq, 3, rho, mu_t);
+                        flux_x = 2.0 * ev * dudx - (2.0 / 3.0) * ev * div_u;
+                        flux_y = ev * (dudy + dvdx);
+                    } else if (ieq == 2) {
+                        double ev = SGS_diffusion(P, &c, ieq, 3, rho, mu_t);
+                        flux_x = ev * (dudy + dvdx);
+                        flux_y = 2.0 * ev * dvdy - (2.0 / 3.0) * ev * div_u;
+                    } else {
+                        double dsdxi = 0, dsdeta = 0;
+                        for (int ii = 0; ii < n; ++ii) {
+                            dsdxi = fma(DPSI(ii, k), LOC3(U, ii, l, ieq), dsdxi);
+                            dsdeta = fma(DPSI(ii, l), LOC3(U, k, ii, ieq), dsdeta);
+                        }
+                        double dsdx = dsdxi * xix + dsdeta * etx;
+                        double dsdy = dsdxi * xiy + dsdeta * ety;
+                        double ed = SGS_diffusion(P, &c, ieq, 3, rho, mu_t);
+                        flux_x = ed * dsdx;
+                        flux_y = ed * dsdy;
+                        if (ieq == 3 && !c.ltheta_eqn) {
+                            /* total-energy equation: viscous work with the momentum viscosity (rhs.jl:2361-2370; micro == 1) */
+                            double ev = SGS_diffusion(P, &c, 1, 3, rho, mu_t);
+                            double txx = 2.0 * ev * dudx - (2.0 / 3.0) * ev * div_u;
+                            double tyy = 2.0 * ev * dvdy - (2.0 / 3.0) * ev * div_u;
+                            double txy = ev * (dudy + dvdx);
+                            double ul = LOC3(U, k, l, 1), vl = LOC3(U, k, l, 2);
+                            flux_x += txx * ul + txy * vl;
+                            flux_y += txy * ul + tyy * vl;
+                        }
+                    }
+                    double gxi = (xix * flux_x + xiy * flux_y) * wJ;
+                    double geta = (etx * flux_x + ety * flux_y) * wJ;
+                    for (int i = 0; i < n; ++i) {
+                        EL4(W->rhs_diff_xi, iel, i, l, ieq) = fma(-DPSI(i, k), gxi, EL4(W->rhs_diff_xi, iel, i, l, ieq));
+                        EL4(W->rhs_diff_eta, iel, k, i, ieq) = fma(-DPSI(i, l), geta, EL4(W->rhs_diff_eta, iel, k, i, ieq));
+                    }
+                }
+            }
+        }
+    }
+    size_t tot = (size_t)E * n * n * q;
+    for (size_t t = 0; t < tot; ++t) W->rhs_diff_el[t] = W->rhs_diff_xi[t] + W->rhs_diff_eta[t];
+}
+
 /*
  * rhs.jl:498-690  _build_rhs!  steps 1-11 (everything up to, not including, DSS_global_RHS!):
  * zero-fill, u2uaux!, Dirichlet BC (mutates u), inviscid element loop, local DSS, AV viscous
@@ -628,7 +1007,9 @@ void jxo_build_rhs_local(const jxo_problem *P, double *u, double *RHS, double ti
         if (P->nsd == 3) memset(W.rhs_diff_zeta, 0, sizeof(double) * el);
         memset(W.rhs_diff_el, 0, sizeof(double) * el);
         memset(W.RHS_visc, 0, sizeof(double) * N * q);
-        if (P->nsd == 3) viscous_rhs_el_3d(P, &W); else viscous_rhs_el_2d(P, &W);   /* rhs.jl:659 */
+        if (P->visc_model) {                                        /* sgs isa AbstractSGSModel: SMAG() / VREM() */
+            if (P->nsd == 3) viscous_rhs_el_3d_sgs(P, &W); else viscous_rhs_el_2d_sgs(P, &W);
+        } else if (P->nsd == 3) viscous_rhs_el_3d(P, &W); else viscous_rhs_el_2d(P, &W);   /* rhs.jl:659 */
         DSS_rhs(P, W.RHS_visc, W.rhs_diff_el);                      /* rhs.jl:671 */
         for (size_t t = 0; t < (size_t)N * q; ++t) RHS[t] = RHS[t] + W.RHS_visc[t];   /* rhs.jl:672 */
     }
@@ -662,6 +1043,14 @@ void jxo_assemble_pack(const double *a, int64_t npoin, int m, const int64_t *idx
 void jxo_assemble_unpack(double *a, int64_t npoin, int m, const int64_t *idx, int64_t len, const double *buf) {
     for (int j = 0; j < m; ++j)
         for (int64_t i = 0; i < len; ++i) a[(idx[i] - 1) + npoin * j] = buf[i * m + j];
+}
+
+/* sgs.μ_turb as the last evaluation left it (each shared node holds the value of the last element that wrote it) */
+const double *jxo_sgs_mu_turb(const jxo_problem *P, double *work) {
+    jxo_work W;
+    memset(&W, 0, sizeof(W));
+    carve(P, work, &W);
+    return W.mu_turb;
 }
 
 double jxo_pow(double x, double y, int mode) { return mode ? jx_pow(x, y) : pow(x, y); }

@@ -73,7 +73,9 @@ class _Problem(ctypes.Structure):
                 ("nx", ctypes.c_void_p), ("ny", ctypes.c_void_p), ("nz", ctypes.c_void_p),
                 ("face_kind", ctypes.c_void_p),
                 ("xmin", ctypes.c_double), ("xmax", ctypes.c_double), ("ymin", ctypes.c_double),
-                ("ymax", ctypes.c_double), ("zmin", ctypes.c_double), ("zmax", ctypes.c_double)]
+                ("ymax", ctypes.c_double), ("zmin", ctypes.c_double), ("zmax", ctypes.c_double),
+                ("visc_model", ctypes.c_int32), ("lrichardson", ctypes.c_int32), ("ltheta_eqn", ctypes.c_int32),
+                ("sgs_pad", ctypes.c_int32), ("sgs", ctypes.c_double * 8), ("ad_lvl", ctypes.c_void_p)]
 
 
 def _f64(a):
@@ -96,7 +98,9 @@ class RefProblem:
     """One rank's `params` as the oracle sees it.  Holds numpy arrays alive for the C struct."""
 
     def __init__(self, sem, qe, *, eq_id=0, lpert=False, lsource=True, lvisc=False, visc_coeff=None,
-                 phys=None, pow_mode=0, neqs=None):
+                 phys=None, pow_mode=0, neqs=None, sgs=None):
+        """sgs: None (AV) or a dict(model="SMAG"|"VREM", delta=mesh.Δeffective_l, lrichardson=True, ltheta_eqn=True,
+        consts=[Pr_t, Sc_t, mu_mol, kappa_mol, Ri_crit, C_s], ad_lvl=None) -- the SGS struct of sgsStructs.jl."""
         m = sem.mesh
         self.sem = sem
         self.neqs = neqs if neqs is not None else m.nsd + 2
@@ -135,11 +139,32 @@ class RefProblem:
         P.nz = keep["nz"].ctypes.data if keep["nz"] is not None else None
         P.face_kind = keep["kind"].ctypes.data
         P.xmin, P.xmax, P.ymin, P.ymax, P.zmin, P.zmax = m.xmin, m.xmax, m.ymin, m.ymax, m.zmin, m.zmax
+        P.visc_model = 0
+        if sgs is not None:
+            P.visc_model = {"SMAG": 1, "VREM": 2}[sgs["model"]]
+            P.lrichardson, P.ltheta_eqn = int(sgs.get("lrichardson", True)), int(sgs.get("ltheta_eqn", True))
+            cs = list(sgs["consts"])
+            assert len(cs) == 6
+            for i in range(6):
+                P.sgs[i] = cs[i]
+            P.sgs[6] = float(sgs["delta"])
+            if sgs.get("ad_lvl") is not None:
+                keep["ad_lvl"] = _i64(sgs["ad_lvl"])
+                assert keep["ad_lvl"].shape == (m.nelem,)
+                P.ad_lvl = keep["ad_lvl"].ctypes.data
         assert lib().jxo_sizeof_problem() == ctypes.sizeof(_Problem)
         self.work = np.empty(lib().jxo_work_doubles(ctypes.byref(P)), np.float64)
 
     def build_rhs_local(self, u, RHS, t):
         lib().jxo_build_rhs_local(ctypes.byref(self.P), u.ctypes.data, RHS.ctypes.data, float(t), self.work.ctypes.data)
+
+    def sgs_mu_turb(self):
+        """sgs.μ_turb after the last evaluation (every shared node holds the value of the last element that wrote it)."""
+        L = lib()
+        L.jxo_sgs_mu_turb.restype = ctypes.c_void_p
+        L.jxo_sgs_mu_turb.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        p = L.jxo_sgs_mu_turb(ctypes.byref(self.P), self.work.ctypes.data)
+        return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_double)), shape=(self.npoin,)).copy()
 
     def divide_by_mass(self, RHS):
         lib().jxo_divide_by_mass_matrix(ctypes.byref(self.P), RHS.ctypes.data)
