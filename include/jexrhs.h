@@ -97,6 +97,20 @@ int jx_version(void);
 int jx_set_problem(jx_ctx *, int nsd, int ngl, int neqs, int64_t nelem, int64_t npoin, int equation_id, int lpert,
                    int lsource, int lvisc, const double *visc_coeff, const double *phys_consts, int nphys);
 
+/* replaces: inputs[:visc_model] = AV() | SMAG() | VREM() -> params.sgs = allocate_SGS(npoin, T, backend, PhysConst, visc_model)
+ * (src/kernel/physics/sgsStructs.jl:77-120) with the flags set at params_setup.jl:249-253, read by compute_sgs_cache! and the
+ * cache-reading SGS_diffusion / _expansion_visc! (SGS.jl:1087-1109, 1118-1685; rhs.jl:2275-2400, 2582-2785).  Call after
+ * jx_set_problem(lvisc = 1) and before jx_upload_mesh.  consts = PhysicalConst's [Pr_t, Sc_t, μ_mol, κ_mol, Ri_crit, C_s]
+ * (globalConstantsPhysics.jl:15-31; g is phys[2]); delta_effective = params.mesh.Δeffective_l (mesh.jl:5632); lrichardson =
+ * get(inputs, :lrichardson, true); ltheta_eqn = !(inputs[:energy_equation] == "energy"); ad_lvl = params.mesh.ad_lvl
+ * (Int64[nelem], 3D only: Δ_effective = ldexp(Δ, -ad_lvl[iel]), rhs.jl:1416) or NULL.  Dry runs only (size(mp.Tabs,1) == 1).
+ * The closures run on the generic element kernel, in both DSS modes, bit-identical to the oracle in the deterministic one. */
+#define JX_VISC_AV 0
+#define JX_VISC_SMAG 1
+#define JX_VISC_VREM 2
+int jx_set_sgs(jx_ctx *, int visc_model, double delta_effective, int lrichardson, int ltheta_eqn, const double *consts,
+               int nconsts, const int64_t *ad_lvl);
+
 /* replaces: params.mesh.connijk, params.mesh.coords, params.metrics.{dξdx..dζdz,Je}, params.basis.dψ,
  * params.ω, params.Minv, params.qp.qe.  metrics: 3D 10 arrays (dξdx dξdy dξdz dηdx dηdy dηdz dζdx dζdy dζdz Je),
  * 2D 5 arrays (dξdx dξdy dηdx dηdy Je), each Float64[nelem, ngl, ngl, ngl|1] element-fastest. */

@@ -19,6 +19,7 @@ HEADER_PATH = os.path.join(_HERE, "..", "include", "jexrhs.h")
 JX_OK, JX_EINVAL, JX_ENODEV, JX_ECUDA, JX_ESTATE, JX_ENCCL, JX_ENOMEM = 0, -1, -2, -3, -4, -5, -6
 JX_OPT_DSS_MODE, JX_OPT_POW_MODE, JX_OPT_ELEM_KERNEL, JX_OPT_CUDA_GRAPH, JX_OPT_OVERLAP = 1, 2, 3, 4, 5
 JX_ELEM_AUTO, JX_ELEM_GENERIC = 0, -1
+JX_VISC_AV, JX_VISC_SMAG, JX_VISC_VREM = 0, 1, 2
 _ERRNAMES = {-1: "JX_EINVAL", -2: "JX_ENODEV", -3: "JX_ECUDA", -4: "JX_ESTATE", -5: "JX_ENCCL", -6: "JX_ENOMEM"}
 
 
@@ -56,6 +57,7 @@ def lib():
     L.jx_last_error.argtypes = [vp, ctypes.c_char_p, i32]
     L.jx_set_option.argtypes = [vp, i32, i64]
     L.jx_set_problem.argtypes = [vp, i32, i32, i32, i64, i64, i32, i32, i32, i32, vp, vp, i32]
+    L.jx_set_sgs.argtypes = [vp, i32, dbl, i32, i32, vp, i32, vp]
     L.jx_upload_mesh.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp]
     L.jx_upload_mesh_coords.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.jx_upload_bcs.argtypes = [vp, i64, vp, vp, vp, vp, vp]
@@ -140,6 +142,13 @@ class Context:
         self.neqs, self.npoin = neqs, npoin
         self._ck(lib().jx_set_problem(self._h, nsd, ngl, neqs, nelem, npoin, eq_id, int(lpert), int(lsource), int(lvisc),
                                       _ptr(v), _ptr(p), len(p)))
+
+    def set_sgs(self, visc_model, delta_effective, lrichardson=True, ltheta_eqn=True, consts=None, ad_lvl=None):
+        """allocate_SGS + the flags of params_setup.jl:249-253 (jx_set_sgs); after set_problem(lvisc=True), before upload_mesh."""
+        cs = f64(consts if consts is not None else np.zeros(0))
+        lv = i64(ad_lvl) if ad_lvl is not None else None
+        self._ck(lib().jx_set_sgs(self._h, int(visc_model), float(delta_effective), int(bool(lrichardson)), int(bool(ltheta_eqn)),
+                                  _ptr(cs), len(cs), _ptr(lv)))
 
     def upload_mesh(self, connijk, coords, metrics, dpsi, omega, Minv, qe):
         mets = [f64(m) for m in metrics]

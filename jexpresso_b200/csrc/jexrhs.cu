@@ -107,6 +107,8 @@ struct jx_ctx {
     int nsd = 0, ngl = 0, neqs = 0, eq_id = 0, lpert = 0, lsource = 0, lvisc = 0;
     int64_t nelem = 0, npoin = 0;
     double visc[8] = {0};
+    SgsArgs sgs;                     // jx_set_sgs: SMAG / VREM closure (model 0 = AV); sgs.ad_lvl points at d_ad_lvl
+    int32_t *d_ad_lvl = nullptr;
     Phys phys;
     const KernelSet *ks = nullptr;
     int np = 0, nmet = 0, rec_bytes = 0;
@@ -269,10 +271,11 @@ void free_halo(jx_ctx *c) {
 
 int select_kernels(jx_ctx *c) {
     const KernelSet *ks = nullptr;
+    const int vcode = c->lvisc ? (c->sgs.model ? 2 : 1) : 0;   // KernelSet::lvisc: 0 inviscid, 1 AV, 2 SGS closure (generic kernel only)
     auto lookup = [&](int variant) -> const KernelSet * {
-        if (c->eq_id == JX_EQ_EULER_THETA && c->nsd == 3) return lookup_euler_theta_3d(c->ngl, c->lpert, c->pow_mode, c->lvisc, variant);
-        if (c->eq_id == JX_EQ_EULER_THETA && c->nsd == 2) return lookup_euler_theta_2d(c->ngl, c->lpert, c->pow_mode, c->lvisc, variant);
-        return lookup_other(c->nsd, c->ngl, c->eq_id, c->lvisc, variant);
+        if (c->eq_id == JX_EQ_EULER_THETA && c->nsd == 3) return lookup_euler_theta_3d(c->ngl, c->lpert, c->pow_mode, vcode, variant);
+        if (c->eq_id == JX_EQ_EULER_THETA && c->nsd == 2) return lookup_euler_theta_2d(c->ngl, c->lpert, c->pow_mode, vcode, variant);
+        return lookup_other(c->nsd, c->ngl, c->eq_id, vcode, variant);
     };
     if (c->elem_variant == JX_ELEM_AUTO) {
         // fastest exact-order kernel that exists for this configuration: the warp-team kernels (bit-identical to the
@@ -289,8 +292,8 @@ int select_kernels(jx_ctx *c) {
         ks = lookup(c->elem_variant == JX_ELEM_GENERIC ? 0 : c->elem_variant);
     }
     if (!ks)
-        return fail(c, JX_EINVAL, "no kernel for nsd=%d ngl=%d eq=%d lpert=%d pow=%d lvisc=%d variant=%d", c->nsd, c->ngl,
-                    c->eq_id, c->lpert, c->pow_mode, c->lvisc, c->elem_variant);
+        return fail(c, JX_EINVAL, "no kernel for nsd=%d ngl=%d eq=%d lpert=%d pow=%d lvisc=%d sgs=%d variant=%d", c->nsd, c->ngl,
+                    c->eq_id, c->lpert, c->pow_mode, c->lvisc, c->sgs.model, c->elem_variant);
     if (ks->neq != c->neqs) return fail(c, JX_EINVAL, "equation set %d has %d equations, got neqs=%d", c->eq_id, ks->neq, c->neqs);
     if (c->have_mesh && (ks->rec_layout != c->rec_layout || ks->visc_layout != c->visc_layout))
         return fail(c, JX_ESTATE, "kernel variant %d reads element-record layout %d/%d, the resident records have layout %d/%d: "
@@ -364,7 +367,7 @@ extern "C" void jx_destroy(jx_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     free_mesh(c); free_bcs(c); free_halo(c);
-    dfree(c->d_gctr);
+    dfree(c->d_gctr); dfree(c->d_ad_lvl);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -425,6 +428,8 @@ extern "C" int jx_set_problem(jx_ctx *c, int nsd, int ngl, int neqs, int64_t nel
     free_mesh(c); free_bcs(c); free_halo(c);
     c->nsd = nsd; c->ngl = ngl; c->neqs = neqs; c->nelem = nelem; c->npoin = npoin;
     c->eq_id = equation_id; c->lpert = lpert ? 1 : 0; c->lsource = lsource ? 1 : 0; c->lvisc = lvisc ? 1 : 0;
+    c->sgs = SgsArgs();              // AV until jx_set_sgs says otherwise
+    dfree(c->d_ad_lvl);
     for (int i = 0; i < 8; ++i) c->visc[i] = (visc_coeff && i < neqs) ? visc_coeff[i] : 0.0;
     for (int i = 0; i < 16; ++i) c->phys.v[i] = (phys_consts && i < nphys) ? phys_consts[i] : 0.0;
     c->np = 1;
@@ -435,6 +440,46 @@ extern "C" int jx_set_problem(jx_ctx *c, int nsd, int ngl, int neqs, int64_t nel
     if ((int64_t)c->np * nelem >= ((int64_t)1 << 32)) return fail(c, JX_EINVAL, "nelem*ngl^nsd must be < 2^32 per rank");
     c->have_problem = true;
     return select_kernels(c);
+}
+
+// replaces: allocate_SGS (sgsStructs.jl:77-120) + the flags of params_setup.jl:249-253
+extern "C" int jx_set_sgs(jx_ctx *c, int visc_model, double delta_effective, int lrichardson, int ltheta_eqn, const double *consts,
+                          int nconsts, const int64_t *ad_lvl) {
+    if (!c) return JX_EINVAL;
+    if (!c->have_problem) return fail(c, JX_ESTATE, "jx_set_sgs before jx_set_problem");
+    if (visc_model < JX_VISC_AV || visc_model > JX_VISC_VREM) return fail(c, JX_EINVAL, "visc_model must be JX_VISC_AV, _SMAG or _VREM");
+    cudaSetDevice(c->device);
+    c->aux_fresh = false; c->acc_ready = false;
+    const SgsArgs old = c->sgs;
+    SgsArgs g;
+    if (visc_model != JX_VISC_AV) {
+        if (!c->lvisc) return fail(c, JX_EINVAL, "an SGS closure needs lvisc = 1 in jx_set_problem");
+        if (!consts || nconsts < 6) return fail(c, JX_EINVAL, "jx_set_sgs: consts = [Pr_t, Sc_t, mu_mol, kappa_mol, Ri_crit, C_s]");
+        if (!(delta_effective > 0.0)) return fail(c, JX_EINVAL, "jx_set_sgs: delta_effective must be positive");
+        g.model = visc_model; g.lrichardson = lrichardson ? 1 : 0; g.ltheta_eqn = ltheta_eqn ? 1 : 0;
+        g.delta = delta_effective;
+        g.Pr_t = consts[0]; g.Sc_t = consts[1]; g.mu_mol = consts[2]; g.kappa_mol = consts[3]; g.Ri_crit = consts[4];
+        g.C_s2 = consts[5] * consts[5];                   // T(PhysConst.C_s * PhysConst.C_s)
+        g.C_vrem = 2.5 * consts[5] * consts[5];           // T(2.5 * PhysConst.C_s * PhysConst.C_s)
+        g.g = c->phys.v[2];
+    }
+    dfree(c->d_ad_lvl);
+    if (visc_model != JX_VISC_AV && ad_lvl && c->nelem > 0) {
+        std::vector<int32_t> lv((size_t)c->nelem);
+        for (int64_t e = 0; e < c->nelem; ++e) {
+            if (ad_lvl[e] < 0 || ad_lvl[e] > 1000) return fail(c, JX_EINVAL, "jx_set_sgs: ad_lvl[%lld] = %lld", (long long)e, (long long)ad_lvl[e]);
+            lv[(size_t)e] = (int32_t)ad_lvl[e];
+        }
+        int rc = dalloc(c, &c->d_ad_lvl, (size_t)c->nelem);
+        if (rc) return rc;
+        CK(cudaMemcpy(c->d_ad_lvl, lv.data(), (size_t)c->nelem * sizeof(int32_t), cudaMemcpyHostToDevice));
+        g.ad_lvl = c->d_ad_lvl;
+    }
+    c->sgs = g;
+    free_split(c);
+    const int rc = select_kernels(c);
+    if (rc) { c->sgs = old; c->sgs.ad_lvl = nullptr; }    // refused (e.g. resident team-kernel records): the AV / previous set stays
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1085,6 +1130,7 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
     ea.atomics = atomics ? 1 : 0; ea.lsource = c->lsource; ea.phys = c->phys;
     for (int i = 0; i < 8; ++i) ea.visc[i] = c->visc[i];
     for (int i = 0; i < 64; ++i) ea.dpsi[i] = c->dpsi[i];
+    ea.sgs = c->sgs;
     // atomics mode folds M^-1 into the scatter weight.  With an interface exchange the ranks then sum already
     // scaled partials (M^-1 is the globally assembled value, identical on every copy of a node): one rounding per
     // contribution instead of one per node, inside the tolerance the unordered mode has anyway, and no extra

@@ -194,6 +194,17 @@ static __global__ void k_bc_dirichlet(BcArgs a) {
 // :1973-2056 2D).  Variant "node": one thread per element node, EPB elements per CTA iteration,
 // element records double-buffered through shared memory by TMA bulk copies.
 // ------------------------------------------------------------------------------------------
+// SGS viscosity: the scalar content of the reference's SGS_SMAG / SGS_VREM structs (sgsStructs.jl:6-72, filled by
+// allocate_SGS :77-120 and params_setup.jl:249-253).  The per-node caches of the reference (sgs.μ_turb ...) are element-local in
+// effect -- compute_sgs_cache! refills them for every element before its equation loop -- so here μ_turb lives in a register.
+struct SgsArgs {
+    int model = 0;                     // 0: AV (sgs === nothing); 1: SMAG; 2: VREM
+    int lrichardson = 0, ltheta_eqn = 1;
+    double delta = 0.0;                // mesh.Δeffective_l
+    double Pr_t = 0, Sc_t = 0, mu_mol = 0, kappa_mol = 0, Ri_crit = 0, C_s2 = 0, C_vrem = 0, g = 0;
+    const int32_t *ad_lvl = nullptr;   // mesh.ad_lvl [nelem] (3D: Δ_effective = ldexp(Δ, -ad_lvl), rhs.jl:1416) or nullptr
+};
+
 struct ElemArgs {
     const double *u;
     const double *qe;
@@ -221,6 +232,7 @@ struct ElemArgs {
     Phys phys;
     double visc[8];
     double dpsi[64];       // Julia dψ[m,i] column-major: dpsi[m + NGL*i]
+    SgsArgs sgs;           // k_elem_node<..., VISC = 2> only
 };
 
 // functors that add the viscous-work term to one equation of the 2D AV pass declare TAU_U_EQ
@@ -233,7 +245,195 @@ struct tau_u_eq { static constexpr int value = -1; };
 template <class EQ>
 struct tau_u_eq<EQ, true> { static constexpr int value = EQ::TAU_U_EQ; };
 
-template <int NSD, int NGL, class EQ, bool VISC, int EPB>
+// Richardson stability function, SGS.jl:1241-1253
+__device__ __forceinline__ double sgs_f_Ri(const SgsArgs &sg, double N2_val, double Sij2_val) {
+    const double Ri = Sij2_val > 1e-12 ? N2_val / Sij2_val : 0.0;
+    if (Ri >= sg.Ri_crit) return 0.0;
+    if (Ri >= 0.0) {
+        const double ratio = Ri / sg.Ri_crit;
+        return (1.0 - ratio) * (1.0 - ratio);
+    }
+    return fmin(sqrt(1.0 - 16.0 * Ri), 3.0);
+}
+
+// cache-reading SGS_diffusion (SGS.jl:1087-1109 3D, :1663-1685 2D); e 0-based, IT = the temperature / energy equation
+template <int IT>
+__device__ __forceinline__ double sgs_diffusion(const SgsArgs &sg, const double *visc, int e, double rho, double mu_turb) {
+    if (e >= 1 && e < IT) return (sg.mu_mol + mu_turb) * visc[e];
+    if (e == IT) {
+        const double k_turb = mu_turb / (rho * sg.Pr_t);
+        if (sg.ltheta_eqn) return k_turb * visc[e];
+        return (sg.kappa_mol + k_turb) * visc[e];
+    }
+    const double k_turb_scalar = mu_turb / (rho * sg.Sc_t);
+    return (sg.kappa_mol + k_turb_scalar) * visc[e];
+}
+
+// Node-local step of the SGS viscous pass for the node (i,j,k) = l of one element: compute_sgs_cache! (SGS.jl:1118-1408 3D,
+// :1416-1655 2D; dry, micro == 1) -- gradients accumulated with separately rounded multiply and add, as the plain Julia loop
+// does -- then the cache-reading _expansion_visc! (rhs.jl:2582-2785 3D, :2275-2400 2D) -- gradients as FMA chains (@turbo) --
+// for every equation.  U: primitives [NEQ][NP] of the element in shared memory; Gv: [NEQ][NSD][NP] weak-form fluxes out.
+template <int NSD, int NGL, int NEQ>
+__device__ __forceinline__ void sgs_node_fluxes(const SgsArgs &sg, double D2, const double *visc, const double *sD, const double *U,
+                                                double *Gv, const double *mt, double wJ, int i, int j, int k, int l) {
+    static_assert(NEQ >= NSD + 2, "SGS closures need (rho, velocity, temperature)");
+    constexpr int NP = Geo<NSD, NGL>::NP;
+    constexpr int IT = NSD + 1;
+    int off[NSD];          // first node of the xi-, eta- (zeta-) line through l, with strides 1, NGL, NGL^2
+    off[0] = NGL * (j + NGL * k);
+    off[1] = i + NGL * NGL * k;
+    if constexpr (NSD == 3) off[2] = i + NGL * j;
+    const int str[3] = {1, NGL, NGL * NGL};
+    const int ijk[3] = {i, j, k};
+    // --- compute_sgs_cache!: velocity and temperature gradients, a += b*c separately rounded
+    double gc[NSD][NSD], gt[NSD];
+#pragma unroll
+    for (int c = 0; c < NSD; ++c) {
+        gt[c] = 0.0;
+#pragma unroll
+        for (int a = 0; a < NSD; ++a) gc[c][a] = 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < NGL; ++m) {
+#pragma unroll
+        for (int a = 0; a < NSD; ++a) {
+            const double dm = sD[m + NGL * ijk[a]];
+            const int ln = off[a] + str[a] * m;
+#pragma unroll
+            for (int c = 0; c < NSD; ++c) gc[c][a] = gc[c][a] + dm * U[(1 + c) * NP + ln];
+            gt[a] = gt[a] + dm * U[IT * NP + ln];
+        }
+    }
+    double Dc[NSD][NSD];   // Dc[c][b] = d u_c / d x_b
+#pragma unroll
+    for (int c = 0; c < NSD; ++c)
+#pragma unroll
+        for (int b = 0; b < NSD; ++b) {
+            if constexpr (NSD == 3) Dc[c][b] = gc[c][0] * mt[b] + gc[c][1] * mt[3 + b] + gc[c][2] * mt[6 + b];
+            else Dc[c][b] = gc[c][0] * mt[b] + gc[c][1] * mt[2 + b];
+        }
+    double Sij2_val;
+    if constexpr (NSD == 3) {
+        const double S12 = 0.5 * (Dc[0][1] + Dc[1][0]), S13 = 0.5 * (Dc[0][2] + Dc[2][0]), S23 = 0.5 * (Dc[1][2] + Dc[2][1]);
+        const double SS = Dc[0][0] * Dc[0][0] + Dc[1][1] * Dc[1][1] + Dc[2][2] * Dc[2][2] + 2.0 * (S12 * S12 + S13 * S13 + S23 * S23);
+        Sij2_val = 2.0 * SS;
+    } else {
+        const double S12 = 0.5 * (Dc[0][1] + Dc[1][0]);
+        const double SS = Dc[0][0] * Dc[0][0] + Dc[1][1] * Dc[1][1] + 2.0 * S12 * S12;
+        Sij2_val = 2.0 * SS;
+    }
+    double f_Ri_val = 1.0;
+    if (sg.lrichardson) {
+        const double th = U[IT * NP + l];
+        double dtdz;                                   // vertical: z in 3D, y in 2D
+        if constexpr (NSD == 3) dtdz = gt[0] * mt[2] + gt[1] * mt[5] + gt[2] * mt[8];
+        else dtdz = gt[0] * mt[1] + gt[1] * mt[3];
+        const double N2_val = fabs(th) > 1e-12 ? (sg.g / th) * dtdz : 0.0;
+        f_Ri_val = sgs_f_Ri(sg, N2_val, Sij2_val);
+    }
+    const double rho = U[l];
+    double mu_turb;
+    if (sg.model == 1) {
+        mu_turb = rho * sg.C_s2 * D2 * sqrt(Sij2_val) * f_Ri_val;
+    } else {
+        double B_b, uu;
+        if constexpr (NSD == 3) {
+            const double b11 = D2 * (Dc[0][0] * Dc[0][0] + Dc[0][1] * Dc[0][1] + Dc[0][2] * Dc[0][2]);
+            const double b12 = D2 * (Dc[0][0] * Dc[1][0] + Dc[0][1] * Dc[1][1] + Dc[0][2] * Dc[1][2]);
+            const double b13 = D2 * (Dc[0][0] * Dc[2][0] + Dc[0][1] * Dc[2][1] + Dc[0][2] * Dc[2][2]);
+            const double b22 = D2 * (Dc[1][0] * Dc[1][0] + Dc[1][1] * Dc[1][1] + Dc[1][2] * Dc[1][2]);
+            const double b23 = D2 * (Dc[1][0] * Dc[2][0] + Dc[1][1] * Dc[2][1] + Dc[1][2] * Dc[2][2]);
+            const double b33 = D2 * (Dc[2][0] * Dc[2][0] + Dc[2][1] * Dc[2][1] + Dc[2][2] * Dc[2][2]);
+            B_b = b11 * b22 + b11 * b33 + b22 * b33 - (b12 * b12 + b13 * b13 + b23 * b23);
+            uu = Dc[0][0] * Dc[0][0] + Dc[0][1] * Dc[0][1] + Dc[0][2] * Dc[0][2] + Dc[1][0] * Dc[1][0] + Dc[1][1] * Dc[1][1] +
+                 Dc[1][2] * Dc[1][2] + Dc[2][0] * Dc[2][0] + Dc[2][1] * Dc[2][1] + Dc[2][2] * Dc[2][2];
+        } else {
+            const double b11 = D2 * (Dc[0][0] * Dc[0][0] + Dc[0][1] * Dc[0][1]);
+            const double b12 = D2 * (Dc[0][0] * Dc[1][0] + Dc[0][1] * Dc[1][1]);
+            const double b22 = D2 * (Dc[1][0] * Dc[1][0] + Dc[1][1] * Dc[1][1]);
+            B_b = b11 * b22 - b12 * b12;
+            uu = Dc[0][0] * Dc[0][0] + Dc[0][1] * Dc[0][1] + Dc[1][0] * Dc[1][0] + Dc[1][1] * Dc[1][1];
+        }
+        const double mu_base = (uu > 2.220446049250313e-16 && B_b > 0.0) ? rho * sg.C_vrem * sqrt(B_b / uu) : 0.0;
+        mu_turb = mu_base * f_Ri_val;
+    }
+    // --- cache-reading _expansion_visc!: velocity gradients again, this time as the @turbo FMA chains
+#pragma unroll
+    for (int c = 0; c < NSD; ++c)
+#pragma unroll
+        for (int a = 0; a < NSD; ++a) gc[c][a] = 0.0;
+#pragma unroll
+    for (int m = 0; m < NGL; ++m) {
+#pragma unroll
+        for (int a = 0; a < NSD; ++a) {
+            const double dm = sD[m + NGL * ijk[a]];
+            const int ln = off[a] + str[a] * m;
+#pragma unroll
+            for (int c = 0; c < NSD; ++c) gc[c][a] = fma(dm, U[(1 + c) * NP + ln], gc[c][a]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NSD; ++c)
+#pragma unroll
+        for (int b = 0; b < NSD; ++b) {
+            if constexpr (NSD == 3) Dc[c][b] = gc[c][0] * mt[b] + gc[c][1] * mt[3 + b] + gc[c][2] * mt[6 + b];
+            else Dc[c][b] = gc[c][0] * mt[b] + gc[c][1] * mt[2 + b];
+        }
+    double div_u;
+    if constexpr (NSD == 3) div_u = Dc[0][0] + Dc[1][1] + Dc[2][2];
+    else div_u = Dc[0][0] + Dc[1][1];
+#pragma unroll
+    for (int e = 0; e < NEQ; ++e) {
+        double flux[NSD];
+        if (e >= 1 && e <= NSD) {
+            const int c = e - 1;
+            const double ev = sgs_diffusion<IT>(sg, visc, e, rho, mu_turb);
+#pragma unroll
+            for (int b = 0; b < NSD; ++b) {
+                if (b == c) flux[b] = 2.0 * ev * Dc[c][c] - (2.0 / 3.0) * ev * div_u;
+                else flux[b] = ev * (Dc[c < b ? c : b][c < b ? b : c] + Dc[c < b ? b : c][c < b ? c : b]);
+            }
+        } else {
+            double gs[NSD];
+#pragma unroll
+            for (int a = 0; a < NSD; ++a) gs[a] = 0.0;
+#pragma unroll
+            for (int m = 0; m < NGL; ++m) {
+#pragma unroll
+                for (int a = 0; a < NSD; ++a) gs[a] = fma(sD[m + NGL * ijk[a]], U[e * NP + off[a] + str[a] * m], gs[a]);
+            }
+            const double ed = sgs_diffusion<IT>(sg, visc, e, rho, mu_turb);
+#pragma unroll
+            for (int b = 0; b < NSD; ++b) {
+                double dsdx;
+                if constexpr (NSD == 3) dsdx = gs[0] * mt[b] + gs[1] * mt[3 + b] + gs[2] * mt[6 + b];
+                else dsdx = gs[0] * mt[b] + gs[1] * mt[2 + b];
+                flux[b] = ed * dsdx;
+            }
+            if constexpr (NSD == 2) {
+                if (e == IT && !sg.ltheta_eqn) {      // total-energy equation: viscous work with the momentum viscosity, rhs.jl:2361-2370
+                    const double ev = sgs_diffusion<IT>(sg, visc, 1, rho, mu_turb);
+                    const double txx = 2.0 * ev * Dc[0][0] - (2.0 / 3.0) * ev * div_u;
+                    const double tyy = 2.0 * ev * Dc[1][1] - (2.0 / 3.0) * ev * div_u;
+                    const double txy = ev * (Dc[0][1] + Dc[1][0]);
+                    const double ul = U[1 * NP + l], vl = U[2 * NP + l];
+                    flux[0] = flux[0] + (txx * ul + txy * vl);
+                    flux[1] = flux[1] + (txy * ul + tyy * vl);
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < NSD; ++a) {
+            double s;
+            if constexpr (NSD == 3) s = mt[3 * a] * flux[0] + mt[3 * a + 1] * flux[1] + mt[3 * a + 2] * flux[2];
+            else s = mt[2 * a] * flux[0] + mt[2 * a + 1] * flux[1];
+            Gv[(e * NSD + a) * NP + l] = s * wJ;       // sigma_mu = 1.0 (rhs.jl:2615): the further factor is exact
+        }
+    }
+}
+
+// VISC: 0 = inviscid only; 1 = AV (constant coefficients, sgs === nothing); 2 = SGS closure (SMAG / VREM, ElemArgs::sgs)
+template <int NSD, int NGL, class EQ, int VISC, int EPB>
 struct ElemNodeCfg {
     using G = Geo<NSD, NGL>;
     static constexpr int NEQ = EQ::NEQ;
@@ -248,7 +448,7 @@ struct ElemNodeCfg {
     static constexpr size_t SMEM_BYTES = (size_t)(SM_REC + SM_FLUX + SM_PRIM + SM_GV + SM_D) * 8 + 16;
 };
 
-template <int NSD, int NGL, class EQ, bool VISC, int EPB>
+template <int NSD, int NGL, class EQ, int VISC, int EPB>
 static __global__ void __launch_bounds__(ElemNodeCfg<NSD, NGL, EQ, VISC, EPB>::NT)
 k_elem_node(const __grid_constant__ ElemArgs a) {
     using C = ElemNodeCfg<NSD, NGL, EQ, VISC, EPB>;
@@ -394,7 +594,16 @@ k_elem_node(const __grid_constant__ ElemArgs a) {
 
         double outv[NEQ];
         if constexpr (VISC) {
-            if (live) {
+            if constexpr (VISC == 2) {
+                if (live) {
+                    double D = a.sgs.delta;
+                    if constexpr (NSD == 3) {
+                        if (a.sgs.ad_lvl) D = ldexp(D, -a.sgs.ad_lvl[iel]);      // calculate_effective_delta, mesh.jl:5749-5751
+                    }
+                    sgs_node_fluxes<NSD, NGL, NEQ>(a.sgs, D * D, a.visc, sD, sU + (size_t)slot * NEQ * NP,
+                                                   sGv + (size_t)slot * NEQ * NSD * NP, mt, mt[NMET - 1], i, j, k, l);
+                }
+            } else if (live) {
                 const double wJ = mt[NMET - 1];
 #pragma unroll
                 for (int e = 0; e < NEQ; ++e) {

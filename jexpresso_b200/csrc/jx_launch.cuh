@@ -10,7 +10,7 @@ constexpr int default_epb() {
     return np >= 256 ? 1 : (256 / np);
 }
 
-template <int NSD, int NGL, class EQ, bool VISC>
+template <int NSD, int NGL, class EQ, int VISC>
 struct NodeKernel {
     static constexpr int EPB = default_epb<NSD, NGL>();
     using C = ElemNodeCfg<NSD, NGL, EQ, VISC, EPB>;
@@ -53,7 +53,7 @@ void launch_gather_t(const GatherArgs &a, cudaStream_t s) {
     k_gather<NEQ><<<(unsigned)((a.npoin + 255) / 256), 256, 0, s>>>(a);
 }
 
-template <int NSD, int NGL, class EQ, bool VISC>
+template <int NSD, int NGL, class EQ, int VISC>
 KernelSet make_node_set(int eq_id, int lpert, int jxpow) {
     using K = NodeKernel<NSD, NGL, EQ, VISC>;
     KernelSet ks;

@@ -11,7 +11,8 @@
 
 ``inputs`` is the reference's ``Dict{Symbol,Any}`` with string keys (``:lvisc`` -> "lvisc",
 ``:μ`` -> "mu", ``:Δt`` -> "dt", ``:SOL_VARS_TYPE`` -> "PERT"|"TOTAL", ``:ode_solver`` ->
-"CarpenterKennedy2N54"|"SSPRK54"|"SSPRK33").  Everything numeric runs in libjexrhs on the GPU
+"CarpenterKennedy2N54"|"SSPRK54"|"SSPRK33", ``:visc_model`` -> "AV"|"SMAG"|"VREM", ``:lrichardson``,
+``:energy_equation`` -> "theta"|"energy").  Everything numeric runs in libjexrhs on the GPU
 through the C ABI (capi.py); this module only marshals arrays.  Semantics kept from the
 reference: ``rhs!`` is in place, returns nothing, and *mutates u* (the Dirichlet projection
 writes the ODE state, BCs.jl:651).
@@ -24,12 +25,13 @@ import numpy as np
 
 from . import capi
 from .physics import (BC_FREE_SLIP, BC_SKIP, EQ_ADVDIFF, EQ_EULER_ENERGY, EQ_EULER_THETA, EQ_EULER_THETA_LES, EQ_SHALLOW_WATER,
-                      SCHEME_CK2N54, SCHEME_SSPRK33, SCHEME_SSPRK54, PhysicalConst)
+                      SCHEME_CK2N54, SCHEME_SSPRK33, SCHEME_SSPRK54, VISC_AV, VISC_SMAG, VISC_VREM, PhysicalConst)
 
 __all__ = ["Params", "params_setup", "rhs_bang", "time_loop_bang", "face_kinds", "float32_dt"]
 
 _PERIODIC_TAGS = {"periodicx", "periodicy", "periodicz", "periodic1", "periodic2", "periodic3", "Laguerre"}
 _SCHEMES = {"CarpenterKennedy2N54": SCHEME_CK2N54, "SSPRK54": SCHEME_SSPRK54, "SSPRK33": SCHEME_SSPRK33}
+_VISC_MODELS = {"AV": VISC_AV, "SMAG": VISC_SMAG, "VREM": VISC_VREM}
 _EQS = {"CompEuler": EQ_EULER_THETA, "CompEulerEnergy": EQ_EULER_ENERGY, "AdvDiff": EQ_ADVDIFF,
         "ShallowWater": EQ_SHALLOW_WATER, "CompEulerLES": EQ_EULER_THETA_LES}
 
@@ -78,6 +80,14 @@ def params_setup(sem, qe, inputs, *, device=0, rank=0, nranks=1, nccl_uid=None, 
         ctx.set_option(capi.JX_OPT_ELEM_KERNEL, elem_kernel)
         ctx.set_option(capi.JX_OPT_OVERLAP, overlap)
         ctx.set_problem(m.nsd, m.ngl, neqs, m.nelem, m.npoin, eq_id, lpert, bool(inputs.get("lsource", False)), lvisc, mu, phys)
+        visc_model = _VISC_MODELS[inputs.get("visc_model", "AV")]
+        if lvisc and visc_model != VISC_AV:
+            # params.sgs = allocate_SGS(...) with the flags of params_setup.jl:249-253.  mesh.Δeffective_l is a global maximum
+            # (mesh.jl:5629-5632): multi-rank callers pass it as inputs["delta_effective"]
+            from .sem import effective_delta_l
+            delta = inputs.get("delta_effective") or effective_delta_l(m)
+            ctx.set_sgs(visc_model, delta, inputs.get("lrichardson", True), inputs.get("energy_equation", "theta") != "energy",
+                        inputs.get("sgs_consts") or PhysicalConst().sgs_packed(), inputs.get("ad_lvl"))
         if device_metrics or device_mass:   # build_metric_terms! on the device (jx_upload_mesh_coords): sem.metrics is not read;
             # device_mass: neither is sem.Minv -- the mass matrix is built, assembled over the halo lists and inverted on the device
             ctx.upload_mesh_coords(m.connijk, m.coords, sem.basis["dpsi"], sem.basis["omega"], None if device_mass else sem.Minv, qe)

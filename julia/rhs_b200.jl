@@ -108,6 +108,17 @@ function b200_setup(params, inputs; device = 0, rank = 0, nranks = 1, uid = C_NU
                    (Ctx, Cint, Cint, Cint, Int64, Int64, Cint, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint),
                    c, nsd, ngl, neqs, mesh.nelem, mesh.npoin, equation_id(inputs), lpert,
                    inputs[:lsource] ? 1 : 0, inputs[:lvisc] ? 1 : 0, μ, phys, length(phys)))
+    # SGS closure (inputs[:visc_model] = SMAG() | VREM(); params.sgs = allocate_SGS(...), params_setup.jl:246-253): the scalar
+    # content of the SGS struct; the per-node caches of the reference live in registers on the device.  Dry runs only.
+    vm = inputs[:visc_model]
+    if inputs[:lvisc] && (vm isa J.SMAG || vm isa J.VREM)
+        size(params.mp.Tabs, 1) == 1 || error("libjexrhs: the SGS closures are implemented for dry runs (no microphysics)")
+        PC = J.PHYS_CONST
+        sgsc = Float64[PC.Pr_t, PC.Sc_t, PC.μ_mol, PC.κ_mol, PC.Ri_crit, PC.C_s]
+        check(c, ccall((:jx_set_sgs, LIB), Cint, (Ctx, Cint, Float64, Cint, Cint, Ptr{Float64}, Cint, Ptr{Int64}),
+                       c, vm isa J.SMAG ? 1 : 2, Float64(mesh.Δeffective_l), get(inputs, :lrichardson, true) ? 1 : 0,
+                       inputs[:energy_equation] == "energy" ? 0 : 1, sgsc, length(sgsc), Int64.(mesh.ad_lvl)))
+    end
     mets = nsd == 3 ?
         [metrics.dξdx, metrics.dξdy, metrics.dξdz, metrics.dηdx, metrics.dηdy, metrics.dηdz,
          metrics.dζdx, metrics.dζdy, metrics.dζdz, metrics.Je] :

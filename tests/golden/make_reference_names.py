@@ -46,7 +46,7 @@ def struct_fields(path, struct):
     names = set()
     for line in m.group(1).split("\n"):
         line = line.split("#")[0].strip()
-        mm = re.match(r"([A-Za-zξηζψωγμΔ_][\wξηζψωγμΔ]*)\s*(::|=)", line)
+        mm = re.match(r"([A-Za-zξηζψωγμκενρλΔ_][\wξηζψωγμκενρλΔ]*)\s*(::|=)", line)
         if mm:
             names.add(mm.group(1))
     return sorted(names)
@@ -59,6 +59,7 @@ out = {
     "St_metrics": struct_fields("src/kernel/mesh/metric_terms.jl", "St_metrics"),
     "AssemblerCache": struct_fields("src/kernel/mpi/mpi_communications.jl", "AssemblerCache"),
     "PhysicalConst": struct_fields("src/kernel/physics/globalConstantsPhysics.jl", "PhysicalConst"),
+    "abstract_types": sorted(set(re.findall(r"^struct\s+(\w+)", read("src/kernel/abstractTypes.jl"), re.M))),
     "rhs_jl_has_PHYS_CONST": "const PHYS_CONST = PhysicalConst{Float64}()" in read("src/kernel/operators/rhs.jl"),
 }
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_names.json"), "w"), indent=1, ensure_ascii=False, sort_keys=True)

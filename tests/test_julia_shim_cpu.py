@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHIM = open(os.path.join(ROOT, "julia", "rhs_b200.jl"), encoding="utf-8").read()
 NAMES = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_names.json"), encoding="utf-8"))
 CODE = "\n".join(line.split("#")[0] for line in SHIM.split("\n"))      # comments stripped
-ID = r"[A-Za-zξηζψωγμΔ_][\wξηζψωγμΔ]*"
+ID = r"[A-Za-zξηζψωγμκενρλΔ_][\wξηζψωγμκενρλΔ]*"
 
 
 def test_params_fields_exist_in_reference():
@@ -36,6 +36,17 @@ def test_struct_fields_exist_in_reference():
         missing = used - set(NAMES[struct])
         assert not missing, f"{var}.* fields missing from the reference's {struct}: {sorted(missing)}"
     assert NAMES["rhs_jl_has_PHYS_CONST"]
+    # the SGS binding reads the closure constants and the mesh's effective resolution / AMR levels
+    assert {"Pr_t", "Sc_t", "μ_mol", "κ_mol", "Ri_crit", "C_s"} <= set(re.findall(r"\bPC\.(" + ID + ")", CODE))
+    assert {"Δeffective_l", "ad_lvl"} <= set(re.findall(r"\bmesh\.(" + ID + ")", CODE))
+
+
+def test_dispatch_tags_exist_in_reference():
+    """`vm isa J.SMAG` etc.: the tag types the shim dispatches on are structs of src/kernel/abstractTypes.jl."""
+    used = set(re.findall(r"\bisa\s+J\.(\w+)", CODE)) | set(re.findall(r"==\s*J\.(\w+)\(\)", CODE))
+    assert {"SMAG", "VREM", "PERT"} <= used
+    missing = used - set(NAMES["abstract_types"])
+    assert not missing, sorted(missing)
 
 
 def test_ccalls_match_the_header():
