@@ -234,7 +234,7 @@ def resolve_overlap(overlap, world, env):
 def workload_name(a):
     nsd, _, _, _, desc = CONFIGS[a.config]
     size = f"{a.nel}^3 elements per GPU" if a.config == "c5" else "whole mesh partitioned over the GPUs"
-    return (f"CompEuler theta {nsd}D TOTAL {'AV mu=125' if a.visc else 'inviscid'} + gravity source, nop={a.nop}, {size} ({desc})")
+    return (f"CompEuler theta {nsd}D TOTAL {('AV mu=125' if a.visc_model == 'AV' else a.visc_model + ' SGS closure') if a.visc else 'inviscid'} + gravity source, nop={a.nop}, {size} ({desc})")
 
 
 def elem_kernel_name(ctx_variant, a):
@@ -243,7 +243,7 @@ def elem_kernel_name(ctx_variant, a):
     return {9: "k_elem_team (fused flux + divergence per element pair; variant 9)",
             8: "k_elem_team (variant 8)",
             12: "k_elem_tri (three-role pencil kernel, nop 7)"}.get(
-        ctx_variant, "k_elem_node (generic fused flux + divergence%s, thread per node)" % (" + AV viscous term" if a.visc else ""))
+        ctx_variant, "k_elem_node (generic fused flux + divergence%s, thread per node)" % ((" + AV viscous term" if a.visc_model == "AV" else " + %s closure" % a.visc_model) if a.visc else ""))
 
 
 def main():
@@ -256,6 +256,9 @@ def main():
     ap.add_argument("--nel", type=int, default=73)
     ap.add_argument("--nop", type=int, default=4)
     ap.add_argument("--visc", action="store_true")
+    ap.add_argument("--visc-model", default="AV", choices=["AV", "SMAG", "VREM"],
+                    help="with --visc: constant coefficients (AV) or an SGS closure (jx_set_sgs; generic element kernel), "
+                         "coefficients of problems/CompEuler/3d/user_inputs.jl:39")
     ap.add_argument("--pert", action="store_true")
     ap.add_argument("--dss-mode", type=int, default=int(os.environ.get("JX_DSS_MODE", "1")))
     ap.add_argument("--pow-mode", type=int, default=int(os.environ.get("JX_POW_MODE", "1")))
@@ -309,6 +312,15 @@ def main():
     N = sem.mesh.npoin
     inputs = {"SOL_VARS_TYPE": "PERT" if a.pert else "TOTAL", "lsource": True, "lvisc": a.visc, "mu": MU3 if nsd == 3 else MU2,
               "dt": 0.1, "ode_solver": "CarpenterKennedy2N54"}
+    if a.visc and a.visc_model != "AV":
+        from jexpresso_b200.sem import element_sizes
+        inputs.update(visc_model=a.visc_model, mu=[0.0, 1.0, 1.0, 1.0, 2.0] if nsd == 3 else [0.0, 1.0, 1.0, 2.0])
+        dmax = float(element_sizes(sem.mesh).max())
+        if world > 1:                               # mesh.Δeffective_l is a global maximum (mesh.jl:5629-5632)
+            tmax = torch.tensor([dmax], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dmax = float(tmax.item())
+        inputs["delta_effective"] = dmax / sem.mesh.nop
     params = jrhs.params_setup(sem, qe, inputs, device=local, rank=rank, nranks=world, nccl_uid=uid,
                                dss_mode=a.dss_mode, pow_mode=a.pow_mode, elem_kernel=a.elem_kernel, overlap=a.overlap)
     ctx = params.ctx

@@ -139,6 +139,23 @@ int jx_condition_state(jx_ctx *, int which);
 int jx_upload_bcs(jx_ctx *, int64_t nfaces, const int64_t *poin_in_bdy_face, const double *nx, const double *ny,
                   const double *nz, const int32_t *face_bc_kind);
 
+/* replaces: inputs[:bdy_fluxes] = true -> apply_boundary_conditions_neumann! -> build_custom_bcs_neumann!(::NSD_3D)
+ * (src/kernel/boundaryconditions/BCs.jl:35-63, 655-816) with the Monin-Obukhov wall model CM_MOST! (src/kernel/physics/CM_MOST.jl:
+ * 69-100, 144-152, 224-261) on the faces tagged "MOST", compute_surface_integral! / DSS_surface_integral!
+ * (src/kernel/boundaryconditions/surface_integral.jl:1-29) and RHS .+= S_flux (rhs.jl:674-689).  3D theta-form CompEuler, dry
+ * (size(mp.Tabs,1) == 1), inputs[:bulk_fluxes] = false.  Arrays as Julia holds them: params.mesh.poin_in_bdy_face [nf,n,n],
+ * params.mesh.bdy_face_in_elem [nf], params.mesh.connijk [E,n,n,n], params.metrics.nx/ny/nz and params.metrics.Jef [nf,n,n],
+ * params.ω [n]; face_flux_kind[f] = JX_FLUX_MOST where bdy_face_type[f] == "MOST", JX_FLUX_NONE elsewhere (user_bc_neumann!
+ * leaves F_surf zero in the shipped decks); inputs[:ifirst_wall_node_index], inputs[:δhf], inputs[:user_heatflux];
+ * most_consts = [PhysConst.karman, z0_m, z0_h] (NULL: 0.4, 0.1, 0.01 -- the literals of BCs.jl:770-772).  After jx_upload_mesh.
+ * Transcendentals are CUDA's: 1e-12 against the oracle, not bit equality.  The interface-first overlap is not used with it. */
+#define JX_FLUX_NONE 0
+#define JX_FLUX_MOST 1
+int jx_upload_bdy_fluxes(jx_ctx *, int64_t nfaces, const int64_t *poin_in_bdy_face, const int64_t *bdy_face_in_elem,
+                         const int64_t *connijk, const double *nx, const double *ny, const double *nz, const double *Jef,
+                         const double *omega, const int32_t *face_flux_kind, int ifirst_wall_node_index, double delta_hf,
+                         double user_heatflux, const double *most_consts, int nconsts);
+
 /* replaces: AssemblerCache built by setup_assembler (src/kernel/mpi/mpi_communications.jl:48-234).
  * CSR by peer rank: send_i (local ids sent to owner r), recv_idx (owner-side local ids the values from r add
  * into), recvback_idx (local ids overwritten with the owner's sum).  Self entries (r == rank) carry the

@@ -20,6 +20,7 @@ JX_OK, JX_EINVAL, JX_ENODEV, JX_ECUDA, JX_ESTATE, JX_ENCCL, JX_ENOMEM = 0, -1, -
 JX_OPT_DSS_MODE, JX_OPT_POW_MODE, JX_OPT_ELEM_KERNEL, JX_OPT_CUDA_GRAPH, JX_OPT_OVERLAP = 1, 2, 3, 4, 5
 JX_ELEM_AUTO, JX_ELEM_GENERIC = 0, -1
 JX_VISC_AV, JX_VISC_SMAG, JX_VISC_VREM = 0, 1, 2
+JX_FLUX_NONE, JX_FLUX_MOST = 0, 1
 _ERRNAMES = {-1: "JX_EINVAL", -2: "JX_ENODEV", -3: "JX_ECUDA", -4: "JX_ESTATE", -5: "JX_ENCCL", -6: "JX_ENOMEM"}
 
 
@@ -63,6 +64,7 @@ def lib():
     L.jx_upload_bcs.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.jx_get_minv.argtypes = [vp, vp]
     L.jx_condition_state.argtypes = [vp, ctypes.c_int]
+    L.jx_upload_bdy_fluxes.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, dbl, dbl, vp, i32]
     L.jx_upload_halo.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.jx_set_state.argtypes = [vp, vp]
     L.jx_get_state.argtypes = [vp, vp]
@@ -180,6 +182,17 @@ class Context:
         a, b = f64(nx), f64(ny)
         cz = f64(nz) if nz is not None else None
         self._ck(lib().jx_upload_bcs(self._h, nf, _ptr(p), _ptr(a), _ptr(b), _ptr(cz), _ptr(k)))
+
+    def upload_bdy_fluxes(self, poin_in_bdy_face, bdy_face_in_elem, connijk, nx, ny, nz, Jef, omega, flux_kinds,
+                          ifirst_wall_node_index, delta_hf=0.0, user_heatflux=0.0, most_consts=None):
+        """inputs[:bdy_fluxes]: the MOST wall model on the faces with flux kind JX_FLUX_MOST (jx_upload_bdy_fluxes)."""
+        p, e, cn = i64(poin_in_bdy_face), i64(bdy_face_in_elem), i64(connijk)
+        a, b, cz, je, om = f64(nx), f64(ny), f64(nz), f64(Jef), f64(omega)
+        k = np.ascontiguousarray(flux_kinds, dtype=np.int32)
+        mc = f64(most_consts) if most_consts is not None else None
+        self._ck(lib().jx_upload_bdy_fluxes(self._h, p.shape[0], _ptr(p), _ptr(e), _ptr(cn), _ptr(a), _ptr(b), _ptr(cz), _ptr(je),
+                                            _ptr(om), _ptr(k), int(ifirst_wall_node_index), float(delta_hf), float(user_heatflux),
+                                            _ptr(mc), 0 if mc is None else len(mc)))
 
     def upload_halo(self, send_i, recv_idx, recvback_idx):
         """Lists indexed by peer rank (1-based local ids), i.e. the AssemblerCache content."""

@@ -16,6 +16,7 @@
 
 #include "../../include/jexrhs.h"
 #include "jx_internal.h"
+#include "jx_bdyflux.cuh"
 
 using namespace jx;
 
@@ -140,6 +141,12 @@ struct jx_ctx {
     double dpsi[64] = {0};
     double *ss[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // SSPRK scratch (uprev, u2, u3, u4, k3)
 
+    // boundary fluxes with the MOST wall model (jx_upload_bdy_fluxes)
+    int nwn = 0, nwnode = 0;          // wall-face nodes, unique wall nodes
+    int32_t *wf_ip1 = nullptr, *wf_ipsfc = nullptr, *wf_node = nullptr, *wf_ptr = nullptr, *wf_hit = nullptr;
+    double *wf_normal = nullptr, *wf_wJ = nullptr, *wf_sface = nullptr;
+    double most_c[3] = {0.4, 0.1, 0.01}, delta_hf = 0.0, user_heatflux = 0.0;
+
     // boundary projection lists
     int nb = 0;
     int32_t *bc_node = nullptr, *bc_ptr = nullptr;
@@ -246,8 +253,15 @@ void free_split(jx_ctx *c) {
     c->n_iface = c->n_inner = 0;
 }
 
+void free_bdy_fluxes(jx_ctx *c) {
+    dfree(c->wf_ip1); dfree(c->wf_ipsfc); dfree(c->wf_node); dfree(c->wf_ptr); dfree(c->wf_hit);
+    dfree(c->wf_normal); dfree(c->wf_wJ); dfree(c->wf_sface);
+    c->nwn = c->nwnode = 0;
+}
+
 void free_mesh(jx_ctx *c) {
     free_split(c);
+    free_bdy_fluxes(c);              // the wall lists name nodes of the mesh they were built for
     dfree(c->u); dfree(c->du); dfree(c->tmp); dfree(c->qe); dfree(c->Minv); dfree(c->coords);
     dfree(c->rhs_el); dfree(c->rhs_el_visc); dfree(c->aux); c->aux_doubles = 0; dfree(c->rec); dfree(c->rec_visc); dfree(c->d_eorig); dfree(c->d_epos); dfree(c->massw); c->mass_pending = false; dfree(c->n2e_ptr); dfree(c->n2e_idx);
     for (auto &p : c->ss) dfree(p);
@@ -259,6 +273,7 @@ void free_bcs(jx_ctx *c) {
     dfree(c->bc_node); dfree(c->bc_ptr); dfree(c->bc_normal);
     c->nb = 0;
 }
+
 void free_halo(jx_ctx *c) {
     free_split(c);
     dfree(c->d_send_i); dfree(c->d_recv_idx); dfree(c->d_recvback_idx); dfree(c->d_sendbuf); dfree(c->d_recvbuf);
@@ -366,7 +381,7 @@ extern "C" void jx_destroy(jx_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
-    free_mesh(c); free_bcs(c); free_halo(c);
+    free_mesh(c); free_bcs(c); free_halo(c); free_bdy_fluxes(c);
     dfree(c->d_gctr); dfree(c->d_ad_lvl);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -425,7 +440,7 @@ extern "C" int jx_set_problem(jx_ctx *c, int nsd, int ngl, int neqs, int64_t nel
     if (npoin >= (int64_t)1 << 31) return fail(c, JX_EINVAL, "npoin must be < 2^31 per rank");
     cudaSetDevice(c->device);
     c->aux_fresh = false; c->acc_ready = false;
-    free_mesh(c); free_bcs(c); free_halo(c);
+    free_mesh(c); free_bcs(c); free_halo(c); free_bdy_fluxes(c);
     c->nsd = nsd; c->ngl = ngl; c->neqs = neqs; c->nelem = nelem; c->npoin = npoin;
     c->eq_id = equation_id; c->lpert = lpert ? 1 : 0; c->lsource = lsource ? 1 : 0; c->lvisc = lvisc ? 1 : 0;
     c->sgs = SgsArgs();              // AV until jx_set_sgs says otherwise
@@ -843,6 +858,77 @@ extern "C" int jx_upload_bcs(jx_ctx *c, int64_t nfaces, const int64_t *poin_in_b
     return JX_OK;
 }
 
+// replaces: inputs[:bdy_fluxes] -> build_custom_bcs_neumann!(::NSD_3D) (BCs.jl:655-816), the surface integrals and RHS .+= S_flux
+extern "C" int jx_upload_bdy_fluxes(jx_ctx *c, int64_t nfaces, const int64_t *poin_in_bdy_face, const int64_t *bdy_face_in_elem,
+                                    const int64_t *connijk, const double *nx, const double *ny, const double *nz, const double *Jef,
+                                    const double *omega, const int32_t *face_flux_kind, int ifirst_wall_node_index, double delta_hf,
+                                    double user_heatflux, const double *most_consts, int nconsts) {
+    if (!c) return JX_EINVAL;
+    if (!c->have_mesh) return fail(c, JX_ESTATE, "jx_upload_bdy_fluxes before jx_upload_mesh");
+    if (c->nsd != 3 || c->neqs < 5) return fail(c, JX_EINVAL, "boundary fluxes: 3D CompEuler equation sets only (rho, rho u, rho v, rho w, rho theta)");
+    if (c->eq_id != JX_EQ_EULER_THETA && c->eq_id != JX_EQ_EULER_THETA_LES) return fail(c, JX_EINVAL, "boundary fluxes: theta-form CompEuler only");
+    cudaSetDevice(c->device);
+    c->aux_fresh = false; c->acc_ready = false;
+    free_bdy_fluxes(c);
+    free_split(c);
+    if (nfaces <= 0) return JX_OK;
+    if (!poin_in_bdy_face || !bdy_face_in_elem || !connijk || !nx || !ny || !nz || !Jef || !omega || !face_flux_kind)
+        return fail(c, JX_EINVAL, "jx_upload_bdy_fluxes: null array");
+    const int n = c->ngl;
+    if (ifirst_wall_node_index < 2 || ifirst_wall_node_index > n) return fail(c, JX_EINVAL, "ifirst_wall_node_index must be in 2..ngl");
+    const int64_t E = c->nelem, N = c->npoin;
+    if (most_consts && nconsts >= 3) { c->most_c[0] = most_consts[0]; c->most_c[1] = most_consts[1]; c->most_c[2] = most_consts[2]; }
+    else { c->most_c[0] = 0.4; c->most_c[1] = 0.1; c->most_c[2] = 0.01; }   // PhysConst.karman; z0_m, z0_h of BCs.jl:770-772
+    c->delta_hf = delta_hf; c->user_heatflux = user_heatflux;
+    // wall-face nodes in the reference's visiting order (face ascending, i outer, j inner) and, per unique wall node, its hits
+    struct Hit { int32_t node; int32_t w; };
+    std::vector<int32_t> ip1, ipsfc;
+    std::vector<double> normal, wJ;
+    std::vector<Hit> hits;
+    const int kw = ifirst_wall_node_index - 1;
+    for (int64_t f = 0; f < nfaces; ++f) {
+        if (face_flux_kind[f] == JX_FLUX_NONE) continue;      // user_bc_neumann!: F_surf stays zero
+        if (face_flux_kind[f] != JX_FLUX_MOST) return fail(c, JX_EINVAL, "face %lld: unknown flux kind %d", (long long)f, face_flux_kind[f]);
+        const int64_t e = bdy_face_in_elem[f] - 1;
+        if (e < 0 || e >= E) return fail(c, JX_EINVAL, "bdy_face_in_elem holds ids outside 1..nelem");
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                const int64_t off = f + nfaces * (i + (int64_t)n * j);
+                const int64_t ip = poin_in_bdy_face[off] - 1;
+                const int64_t a1 = connijk[e + E * (i + n * (j + n * (int64_t)kw))] - 1;
+                const int64_t as = connijk[e + E * (i + n * (int64_t)j)] - 1;
+                if (ip < 0 || ip >= N || a1 < 0 || a1 >= N || as < 0 || as >= N) return fail(c, JX_EINVAL, "node ids outside 1..npoin");
+                hits.push_back({(int32_t)ip, (int32_t)ip1.size()});
+                ip1.push_back((int32_t)a1); ipsfc.push_back((int32_t)as);
+                normal.push_back(nx[off]); normal.push_back(ny[off]); normal.push_back(nz[off]);
+                const double w = omega[i] * omega[j];
+                wJ.push_back(w * Jef[off]);                    // surface_integral.jl:4: ω[i]*ω[j]*Jac_face[i,j]
+            }
+    }
+    if (ip1.empty()) return JX_OK;
+    std::stable_sort(hits.begin(), hits.end(), [](const Hit &x, const Hit &y) { return x.node < y.node; });
+    std::vector<int32_t> node, ptr, hit(hits.size());
+    for (size_t h = 0; h < hits.size(); ++h) {
+        if (h == 0 || hits[h].node != hits[h - 1].node) { node.push_back(hits[h].node); ptr.push_back((int32_t)h); }
+        hit[h] = hits[h].w;
+    }
+    ptr.push_back((int32_t)hits.size());
+    int rc;
+    if ((rc = dalloc(c, &c->wf_ip1, ip1.size())) || (rc = dalloc(c, &c->wf_ipsfc, ipsfc.size())) || (rc = dalloc(c, &c->wf_node, node.size())) ||
+        (rc = dalloc(c, &c->wf_ptr, ptr.size())) || (rc = dalloc(c, &c->wf_hit, hit.size())) || (rc = dalloc(c, &c->wf_normal, normal.size())) ||
+        (rc = dalloc(c, &c->wf_wJ, wJ.size())) || (rc = dalloc(c, &c->wf_sface, ip1.size() * 4)))
+        return rc;
+    CK(cudaMemcpy(c->wf_ip1, ip1.data(), ip1.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->wf_ipsfc, ipsfc.data(), ipsfc.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->wf_node, node.data(), node.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->wf_ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->wf_hit, hit.data(), hit.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->wf_normal, normal.data(), normal.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->wf_wJ, wJ.data(), wJ.size() * 8, cudaMemcpyHostToDevice));
+    c->nwn = (int)ip1.size(); c->nwnode = (int)node.size();
+    return JX_OK;
+}
+
 extern "C" int jx_upload_halo(jx_ctx *c, const int64_t *send_ptr, const int64_t *send_i, const int64_t *recv_ptr,
                               const int64_t *recv_idx, const int64_t *recvback_ptr, const int64_t *recvback_idx) {
     if (!c) return JX_EINVAL;
@@ -1180,7 +1266,22 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
         }
     };
     ea.glist = nullptr; ea.gctr = nullptr; ea.nlist = 0; ea.reserve_sms = 0; ea.exit_ctr = nullptr; ea.exit_budget = 0;
-    const bool split = atomics && c->have_halo && c->split_ready && c->n_iface > 0 && ks->has_dyn && E > 0;
+    const bool bdy = c->nwn > 0;                                         // boundary fluxes: added before the exchange, rhs.jl:674-689
+    auto bdy_fluxes = [&]() {
+        PhaseScope ps(c, PH_BC);
+        MostArgs ma;
+        ma.u = u; ma.qe = c->qe; ma.coords = c->coords; ma.ip1 = c->wf_ip1; ma.ipsfc = c->wf_ipsfc; ma.normal = c->wf_normal;
+        ma.wJ = c->wf_wJ; ma.sface = c->wf_sface; ma.npoin = N; ma.nwn = c->nwn; ma.lpert = c->lpert;
+        ma.karman = c->most_c[0]; ma.z0_m = c->most_c[1]; ma.z0_h = c->most_c[2]; ma.cp = c->phys.v[4]; ma.g = c->phys.v[2];
+        ma.delta_hf = c->delta_hf; ma.user_heatflux = c->user_heatflux;
+        k_most_faces<<<nblk(c->nwn, 128), 128, 0, s>>>(ma);
+        FluxAddArgs fa;
+        fa.rhs = acc; fa.Minv = fold_minv ? c->Minv : nullptr; fa.sface = c->wf_sface; fa.node = c->wf_node; fa.ptr = c->wf_ptr;
+        fa.hit = c->wf_hit; fa.npoin = N; fa.nnode = c->nwnode;
+        k_bdy_flux_add<<<nblk(c->nwnode, 128), 128, 0, s>>>(fa);
+        c->launches += 2;
+    };
+    const bool split = atomics && c->have_halo && c->split_ready && c->n_iface > 0 && ks->has_dyn && E > 0 && !bdy;
     if (split) {
         // interface groups first; their sums are final once that launch ends, so the exchange (second stream, high
         // priority) runs beside the launch over the interior groups, which leaves overlap_sms SMs to it
@@ -1257,23 +1358,22 @@ int rhs_core(jx_ctx *c, double *u, double *du, const StageUpdate &upd) {
         g.rhs_el = c->rhs_el; g.rhs_el_visc = c->lvisc ? c->rhs_el_visc : nullptr; g.ptr = c->n2e_ptr; g.idx = c->n2e_idx;
         g.Minv = c->Minv; g.out = du; g.u = u; g.tmp = c->tmp; g.npoin = N; g.np = c->np; g.neqs = q;
         g.A = upd.A; g.B = upd.B; g.dt = upd.dt; g.first_stage = upd.first;
-        g.mode = c->have_halo ? 0 : (upd.kind == 1 ? 2 : 1);            // rhs.jl:624, 671-672, 698-699
+        g.mode = (c->have_halo || bdy) ? 0 : (upd.kind == 1 ? 2 : 1);   // rhs.jl:624, 671-672, 698-699
         ks->launch_gather(g, s);
         c->launches++;
-        if (!c->have_halo) { CK(cudaGetLastError()); return JX_OK; }
+        if (!c->have_halo && !bdy) { CK(cudaGetLastError()); return JX_OK; }
     }
+    if (bdy) bdy_fluxes();                                               // apply_boundary_conditions_neumann!, rhs.jl:674-689
     if (c->have_halo) {                                                  // DSS_global_RHS!, rhs.jl:690
-        {
-            PhaseScope ps(c, PH_HALO);
-            int rc = assemble(c, acc, s, 0);
-            if (rc) return rc;
-            restore_iface();
-        }
-        if (!fold_minv) {
-            PhaseScope ps(c, PH_UPDATE);
-            k_scale_minv<<<nblk(N * q, 256), 256, 0, s>>>(du, c->Minv, N, q);   // rhs.jl:698-699
-            c->launches++;
-        }
+        PhaseScope ps(c, PH_HALO);
+        int rc = assemble(c, acc, s, 0);
+        if (rc) return rc;
+        restore_iface();
+    }
+    if ((c->have_halo || bdy) && !fold_minv) {
+        PhaseScope ps(c, PH_UPDATE);
+        k_scale_minv<<<nblk(N * q, 256), 256, 0, s>>>(du, c->Minv, N, q);   // rhs.jl:698-699
+        c->launches++;
     }
     if (upd.kind != 0) stage_update();
     CK(cudaGetLastError());

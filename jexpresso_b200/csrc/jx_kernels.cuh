@@ -449,7 +449,7 @@ struct ElemNodeCfg {
 };
 
 template <int NSD, int NGL, class EQ, int VISC, int EPB>
-static __global__ void __launch_bounds__(ElemNodeCfg<NSD, NGL, EQ, VISC, EPB>::NT)
+static __global__ void __launch_bounds__(ElemNodeCfg<NSD, NGL, EQ, VISC, EPB>::NT, (VISC == 2 && ElemNodeCfg<NSD, NGL, EQ, VISC, EPB>::NT <= 256) ? 2 : 1)
 k_elem_node(const __grid_constant__ ElemArgs a) {
     using C = ElemNodeCfg<NSD, NGL, EQ, VISC, EPB>;
     using G = Geo<NSD, NGL>;

@@ -12,7 +12,8 @@
 ``inputs`` is the reference's ``Dict{Symbol,Any}`` with string keys (``:lvisc`` -> "lvisc",
 ``:μ`` -> "mu", ``:Δt`` -> "dt", ``:SOL_VARS_TYPE`` -> "PERT"|"TOTAL", ``:ode_solver`` ->
 "CarpenterKennedy2N54"|"SSPRK54"|"SSPRK33", ``:visc_model`` -> "AV"|"SMAG"|"VREM", ``:lrichardson``,
-``:energy_equation`` -> "theta"|"energy").  Everything numeric runs in libjexrhs on the GPU
+``:energy_equation`` -> "theta"|"energy", ``:bdy_fluxes``, ``:ifirst_wall_node_index``, ``:δhf`` -> "delta_hf",
+``:user_heatflux``).  Everything numeric runs in libjexrhs on the GPU
 through the C ABI (capi.py); this module only marshals arrays.  Semantics kept from the
 reference: ``rhs!`` is in place, returns nothing, and *mutates u* (the Dirichlet projection
 writes the ODE state, BCs.jl:651).
@@ -95,6 +96,15 @@ def params_setup(sem, qe, inputs, *, device=0, rank=0, nranks=1, nccl_uid=None, 
             ctx.upload_mesh(m.connijk, m.coords, sem.metric_list, sem.basis["dpsi"], sem.basis["omega"], sem.Minv, qe)
         if m.poin_in_bdy_face.shape[0] > 0:
             ctx.upload_bcs(m.poin_in_bdy_face, sem.nx, sem.ny, sem.nz, face_kinds(m.bdy_face_type))
+        if inputs.get("bdy_fluxes", False):
+            # apply_boundary_conditions_neumann! (BCs.jl:35-63, 655-816): MOST wall model on the faces tagged "MOST";
+            # metrics.Jef comes with the SEM bundle (sem.extra["Jef"]) or is built here from the face coordinates
+            from .sem.metrics import boundary_face_jacobian
+            Jef = sem.extra.get("Jef") if sem.extra.get("Jef") is not None else boundary_face_jacobian(m, sem.basis)
+            kinds = np.array([capi.JX_FLUX_MOST if t == "MOST" else capi.JX_FLUX_NONE for t in m.bdy_face_type], np.int32)
+            ctx.upload_bdy_fluxes(m.poin_in_bdy_face, m.bdy_face_in_elem, m.connijk, sem.nx, sem.ny, sem.nz, Jef, sem.basis["omega"],
+                                  kinds, inputs["ifirst_wall_node_index"], inputs.get("delta_hf", 0.0),
+                                  inputs.get("user_heatflux", 0.0), inputs.get("most_consts"))
         if sem.asm is not None and not sem.asm.is_trivial():
             ctx.upload_halo(sem.asm.send_i, sem.asm.recv_idx, sem.asm.recvback_idx)
     except Exception:

@@ -43,6 +43,9 @@ class BoxSpec:
     periodic: tuple = (False, False, False)
     tags: dict = field(default_factory=dict)   # side name -> tag, default "free_slip"
     warp: float = 0.0     # amplitude (fraction of the element size) of the smooth interior warp
+    wall_aligned: tuple = ()   # 3D, "ymin" only: the faces of that side are listed in the element's own (i, j) order at local
+                               # k = 1 (poin_in_bdy_face[f, i, j] = connijk[e, i, j, 1]) -- what the wall-model loop of
+                               # build_custom_bcs_neumann! assumes when it walks connijk[e, i, j, ifirst_wall_node] (BCs.jl:703-717)
 
 
 @dataclass
@@ -301,7 +304,11 @@ def _box3d(spec, xi, sub, rank, nranks):
             idx[fixed_axis] = np.full((n, n), fixed_idx)
             idx[t1_of] = (base[t1_of] + a)[:, None] + np.zeros((n, n), np.int64)
             idx[t2_of] = (base[t2_of] + a)[None, :] + np.zeros((n, n), np.int64)
-            faces.append(lid[idx[0], idx[1], idx[2]] + 1)
+            if side in spec.wall_aligned:
+                assert side == "ymin", "wall_aligned: local k runs along +y (mesh.jl:2194-2201), so only the ymin side qualifies"
+                faces.append(np.array(connijk[e, :, :, 0]))
+            else:
+                faces.append(lid[idx[0], idx[1], idx[2]] + 1)
             ftype.append(tag)
             fel.append(e + 1)
 

@@ -177,3 +177,26 @@ def boundary_normals(mesh):
     nx[flip] = -nx[flip]
     ny[flip] = -ny[flip]
     return nx, ny, None
+
+
+def boundary_face_jacobian(mesh, basis):
+    """metrics.Jef Float64[nfaces_bdy, ngl, ngl] (metric_terms.jl:479-570): the surface Jacobian of every boundary-face node,
+    |x_xi x x_eta| with the face coordinates differentiated along the two face directions (psi is the identity at the LGL
+    nodes).  An input array of the boundary-flux path (params.metrics.Jef); host-side test support like the rest of sem/."""
+    assert mesh.nsd == 3
+    P = mesh.poin_in_bdy_face - 1
+    nf, n = P.shape[0], mesh.ngl
+    Jef = np.zeros((nf, n, n), order="F")
+    if nf == 0:
+        return Jef
+    dpsi = np.asarray(basis["dpsi"])                       # dpsi[i, k] = L'_i(xi_k)
+    d = {}
+    for name, c in (("x", mesh.x), ("y", mesh.y), ("z", mesh.z)):
+        f = c[P]                                           # [face, i, j]
+        d[name + "xi"] = np.einsum("ik,fil->fkl", dpsi, f)
+        d[name + "eta"] = np.einsum("jl,fkj->fkl", dpsi, f)
+    a = d["yeta"] * d["zxi"] - d["yxi"] * d["zeta"]
+    b = d["xxi"] * d["zeta"] - d["xeta"] * d["zxi"]
+    c_ = d["xeta"] * d["yxi"] - d["xxi"] * d["yeta"]
+    Jef[...] = np.sqrt(a * a + b * b + c_ * c_)
+    return Jef

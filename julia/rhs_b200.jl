@@ -144,6 +144,21 @@ function b200_setup(params, inputs; device = 0, rank = 0, nranks = 1, uid = C_NU
         check(c, ccall((:jx_upload_bcs, LIB), Cint, (Ctx, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
                        c, size(mesh.poin_in_bdy_edge, 1), mesh.poin_in_bdy_edge, metrics.nx, metrics.ny, C_NULL, kinds))
     end
+    # Boundary fluxes (inputs[:bdy_fluxes]; apply_boundary_conditions_neumann!, BCs.jl:35-63, 655-816): the MOST wall model on the
+    # faces tagged "MOST", surface integrals and RHS .+= S_flux on the device.  Dry runs, bulk_fluxes = false.
+    if nsd == 3 && inputs[:bdy_fluxes]
+        inputs[:bulk_fluxes] && error("libjexrhs: bulk surface fluxes need the microphysics state (not on the device path)")
+        size(params.mp.Tabs, 1) == 1 || error("libjexrhs: the wall model is implemented for dry runs (no microphysics)")
+        PC = J.PHYS_CONST
+        fk = Int32[t == "MOST" ? 1 : 0 for t in mesh.bdy_face_type]
+        mostc = Float64[PC.karman, 0.1, 0.01]                                 # z0_m, z0_h: the literals of BCs.jl:770-772
+        check(c, ccall((:jx_upload_bdy_fluxes, LIB), Cint,
+                       (Ctx, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                        Ptr{Float64}, Ptr{Int32}, Cint, Float64, Float64, Ptr{Float64}, Cint),
+                       c, size(mesh.poin_in_bdy_face, 1), mesh.poin_in_bdy_face, mesh.bdy_face_in_elem, mesh.connijk,
+                       metrics.nx, metrics.ny, metrics.nz, metrics.Jef, params.ω, fk, inputs[:ifirst_wall_node_index],
+                       Float64(inputs[:δhf]), Float64(inputs[:user_heatflux]), mostc, length(mostc)))
+    end
     # AssemblerCache (mpi_communications.jl:48-73).  Uploaded whenever its lists are non-empty -- also on ONE rank, where
     # periodic twins are summed by the reference's MPI self-send (mpi_communications.jl:99-112).
     cache = params.g_dss_cache

@@ -74,6 +74,15 @@ typedef struct {
     int32_t sgs_pad;
     double sgs[8];            /* Pr_t, Sc_t, mu_mol, kappa_mol, Ri_crit, C_s of PhysicalConst; [6] = mesh.Δeffective_l (mesh.jl:5632) */
     const int64_t *ad_lvl;    /* mesh.ad_lvl [nelem] (calculate_effective_delta, mesh.jl:5749-5751) or NULL = all zero */
+    /* boundary fluxes: build_custom_bcs_neumann!(::NSD_3D), BCs.jl:655-816 with inputs[:bdy_fluxes] = true,
+     * inputs[:bulk_fluxes] = false, dry (size(mp.Tabs,1) == 1) */
+    int32_t lbdy_fluxes;             /* inputs[:bdy_fluxes] */
+    int32_t ifirst_wall_node;        /* inputs[:ifirst_wall_node_index] (1-based, 2 <= . <= ngl) */
+    double delta_hf, user_heatflux;  /* inputs[:δhf], inputs[:user_heatflux] */
+    double most[4];                  /* PhysConst.karman, z0_m, z0_h (the literals 0.1, 0.01 of BCs.jl:770-772), unused */
+    const int64_t *bdy_face_in_elem; /* [nfb] */
+    const double *Jef;               /* metrics.Jef [nfb, ngl, ngl] */
+    const int32_t *face_flux_kind;   /* [nfb]: 1 = bdy_face_type == "MOST"; 0 = user_bc_neumann! (leaves F_surf zero in the decks) */
 } jxo_problem;
 
 static inline double eos_pow(const jxo_problem *P, double base, double expo) {
@@ -292,6 +301,8 @@ typedef struct {
     double *RHS_visc;  /* [npoin, neqs] */
     double *F, *G, *H, *S, *uprim; /* [n^d, neqs(+1)] */
     double *mu_turb;   /* sgs.μ_turb [npoin]: per-node cache, overwritten element by element (SGS.jl:1257, 1405) */
+    double *S_face;    /* [nfb, ngl, ngl, neqs] */
+    double *S_flux;    /* [npoin, neqs] */
 } jxo_work;
 
 size_t jxo_work_doubles(const jxo_problem *P) {
@@ -301,6 +312,7 @@ size_t jxo_work_doubles(const jxo_problem *P) {
     if (P->lvisc) tot += 4 * el + (size_t)P->npoin * P->neqs;
     tot += 4 * nd * P->neqs + nd * (P->neqs + 1);
     if (P->lvisc && P->visc_model) tot += (size_t)P->npoin;
+    if (P->lbdy_fluxes) tot += (size_t)P->nfaces_bdy * n * n * P->neqs + (size_t)P->npoin * P->neqs;
     return tot;
 }
 
@@ -322,6 +334,11 @@ static void carve(const jxo_problem *P, double *mem, jxo_work *W) {
     W->S = mem; mem += nd * P->neqs;
     W->uprim = mem; mem += nd * (P->neqs + 1);
     W->mu_turb = (P->lvisc && P->visc_model) ? mem : NULL;
+    if (W->mu_turb) mem += (size_t)P->npoin;
+    if (P->lbdy_fluxes) {
+        W->S_face = mem; mem += (size_t)P->nfaces_bdy * n * n * P->neqs;
+        W->S_flux = mem;
+    }
 }
 
 /* rhs.jl:29-47 u2uaux! / uaux2u! */
@@ -971,6 +988,130 @@ static void viscous_rhs_el_2d_sgs(const jxo_problem *P, jxo_work *W) {
     for (size_t t = 0; t < tot; ++t) W->rhs_diff_el[t] = W->rhs_diff_xi[t] + W->rhs_diff_eta[t];
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Boundary fluxes with the Monin-Obukhov wall model (second part).  PARITY UNPINNED (no golden vector of a
+ * bdy_fluxes deck); cross-checked against an independent numpy transcription in tests/test_bdy_flux_cpu.py.
+ * CM_MOST.jl: Businger-Dyer functions and the fixed-point iteration for (u*, theta*); log / atan / pow are libm's here,
+ * Julia's in the reference, CUDA's on the device: <= 2 ulp apart, so this path is held to 1e-12, not to bit equality.
+ * ------------------------------------------------------------------------------------------ */
+/* CM_MOST.jl:224-244 psi_m, psi_h (a_m = a_h = 16, b_m = b_h = 5, :69-72) */
+static double most_psi_m(double zeta) {
+    if (zeta < 0) {
+        double x = pow(1 - 16.0 * zeta, 0.25);
+        return 2 * log((1 + x) / 2) + log((1 + x * x) / 2) - 2 * atan(x) + 3.141592653589793 / 2;
+    }
+    return -5.0 * zeta;
+}
+static double most_psi_h(double zeta) {
+    if (zeta < 0) {
+        double y = pow(1 - 16.0 * zeta, 0.5);
+        return 2 * log((1 + y) / 2);
+    }
+    return -5.0 * zeta;
+}
+/* CM_MOST.jl:256-261 */
+static double most_obukhov_length(double u_star, double T_ref, double Q_H, double cp, double karman, double g) {
+    if (fabs(Q_H) < 1e-6) return 1e6;
+    return -(u_star * u_star * u_star) * T_ref * cp / (karman * g * Q_H);
+}
+/* CM_MOST.jl:77-100 _surface_scales_dry */
+static void most_surface_scales_dry(double u_ref, double theta_ref, double z_ref, double theta_s, double z0_m, double z0_h,
+                                    double karman, double cp, double g, double rho, double *u_star_out, double *theta_star_out) {
+    double u_star = karman * u_ref / log(z_ref / z0_m);
+    double theta_star = karman * (theta_ref - theta_s) / log(z_ref / z0_h);
+    double Q_H = -rho * cp * u_star * theta_star;
+    double L = most_obukhov_length(u_star, theta_ref, Q_H, cp, karman, g);
+    for (int it = 0; it < 20; ++it) {
+        double zeta = z_ref / L, zeta0_m = z0_m / L, zeta0_h = z0_h / L;
+        double u_star_new = karman * u_ref / (log(z_ref / z0_m) - most_psi_m(zeta) + most_psi_m(zeta0_m));
+        double theta_star_new = karman * (theta_ref - theta_s) / (log(z_ref / z0_h) - most_psi_h(zeta) + most_psi_h(zeta0_h));
+        double Q_H_new = -rho * cp * u_star_new * theta_star_new;
+        double L_new = most_obukhov_length(u_star_new, theta_ref, Q_H_new, cp, karman, g);
+        double err = fabs(L_new - L) / fmax(fabs(L), fabs(L_new));
+        u_star = u_star_new; theta_star = theta_star_new; Q_H = Q_H_new; L = L_new;
+        if (err < 1e-4) break;
+    }
+    *u_star_out = u_star; *theta_star_out = theta_star;
+}
+/* CM_MOST.jl:144-152 CM_MOST! (dry, positional z0_m, z0_h) */
+static void CM_MOST(double *tau_f, double *wtheta, double rho, double u_ref, double v_ref, double w_ref, double theta_ref,
+                    double theta_s, double z_ref, double karman, double cp, double g, double z0_m, double z0_h) {
+    double u_magnitude = sqrt(u_ref * u_ref + v_ref * v_ref + w_ref * w_ref);
+    double u_star, theta_star;
+    most_surface_scales_dry(u_magnitude, theta_ref, z_ref, theta_s, z0_m, z0_h, karman, cp, g, rho, &u_star, &theta_star);
+    double tau_magnitude = rho * (u_star * u_star);
+    tau_f[0] = -tau_magnitude * (u_ref / (u_magnitude + 2.22e-16));
+    tau_f[1] = -tau_magnitude * (v_ref / (u_magnitude + 2.22e-16));
+    tau_f[2] = -tau_magnitude * (w_ref / (u_magnitude + 2.22e-16));
+    wtheta[0] = -u_star * theta_star;
+}
+
+#define FACE3(a, iface, i, j) (a)[(iface) + nf * ((i) + n * (int64_t)(j))]
+/* BCs.jl:655-816 build_custom_bcs_neumann!(::NSD_3D) with lbdy_fluxes, !lbulk_fluxes, micro == 1; surface_integral.jl:1-29
+ * compute_surface_integral! + DSS_surface_integral!; RHS .+= S_flux.  resetbdyfluxToZero! (rhs.jl:105-109) first. */
+static void apply_boundary_conditions_neumann_3d(const jxo_problem *P, jxo_work *W, double *RHS) {
+    const int n = P->ngl, q = P->neqs;
+    const int64_t E = P->nelem, N = P->npoin, nf = P->nfaces_bdy;
+    const int64_t *conn = P->connijk;
+    const double *om = P->omega;
+    const double karman = P->most[0], z0_m = P->most[1], z0_h = P->most[2], cp = P->phys[4], g = P->phys[2];
+    const int kw = P->ifirst_wall_node - 1;
+    double F_surf[8 * 8 * 8];
+    memset(W->S_face, 0, sizeof(double) * nf * n * n * q);
+    memset(W->S_flux, 0, sizeof(double) * N * q);
+    for (int64_t iface = 0; iface < nf; ++iface) {
+        memset(F_surf, 0, sizeof(double) * n * n * q);
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) {
+            const int64_t e = P->bdy_face_in_elem[iface] - 1;
+            const int64_t ip1 = CONN3(e, i, j, kw) - 1;           /* inside point */
+            if (P->face_flux_kind[iface] == 1) {                  /* bdy_face_type[iface] == "MOST" */
+                const int64_t ipsfc = CONN3(e, i, j, 0) - 1;
+                double rho, u_in, v_in, w_in, th_in, th_sfc;
+                const double *ua = W->uaux, *qe = P->qe;
+                if (!P->lpert) {
+                    rho = ua[ip1];
+                    u_in = ua[ip1 + N * 1] / rho; v_in = ua[ip1 + N * 2] / rho; w_in = ua[ip1 + N * 3] / rho;
+                    th_in = ua[ip1 + N * 4] / rho;
+                    th_sfc = ua[ipsfc + N * 4] / ua[ipsfc];
+                } else {
+                    rho = ua[ip1] + qe[ip1];
+                    u_in = (ua[ip1 + N * 1] + qe[ip1 + N * 1]) / rho;
+                    v_in = (ua[ip1 + N * 2] + qe[ip1 + N * 2]) / rho;
+                    w_in = (ua[ip1 + N * 3] + qe[ip1 + N * 3]) / rho;
+                    th_in = (ua[ip1 + N * 4] + qe[ip1 + N * 4]) / rho;
+                    th_sfc = (ua[ipsfc + N * 4] + qe[ipsfc + N * 4]) / (ua[ipsfc] + qe[ipsfc]);
+                }
+                const double nx = FACE3(P->nx, iface, i, j), ny = FACE3(P->ny, iface, i, j), nz = FACE3(P->nz, iface, i, j);
+                double vproj = u_in * nx + v_in * ny + w_in * nz;
+                u_in = u_in - vproj * nx; v_in = v_in - vproj * ny; w_in = w_in - vproj * nz;
+                double dx = P->coords[0 + 3 * ip1] - P->coords[0 + 3 * ipsfc];
+                double dy = P->coords[1 + 3 * ip1] - P->coords[1 + 3 * ipsfc];
+                double dz = P->coords[2 + 3 * ip1] - P->coords[2 + 3 * ipsfc];
+                double z_inside = fabs(dx * nx + dy * ny + dz * nz);
+                double tau_f[3], wth[1];
+                CM_MOST(tau_f, wth, rho, u_in, v_in, w_in, th_in, th_sfc, z_inside, karman, cp, g, z0_m, z0_h);
+                F_surf[i + n * (j + n * 1)] = tau_f[0];
+                F_surf[i + n * (j + n * 2)] = tau_f[1];
+                F_surf[i + n * (j + n * 3)] = tau_f[2];
+                F_surf[i + n * (j + n * 4)] = wth[0] * (1.0 - P->delta_hf) + P->user_heatflux * P->delta_hf;
+            }
+            /* else: user_bc_neumann! -- an empty hook in problems/CompEuler/LESICP1/user_bc.jl:45-100 (all commented out) and
+             * zero writes in problems/CompEuler/3d/user_bc.jl:35-42: F_surf stays zero */
+        }
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) {
+            double wJ = om[i] * om[j] * FACE3(P->Jef, iface, i, j);
+            for (int k = 0; k < q; ++k)
+                W->S_face[iface + nf * (i + n * (j + n * (int64_t)k))] += wJ * F_surf[i + n * (j + n * k)];
+        }
+    }
+    for (int64_t iface = 0; iface < nf; ++iface)
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) {
+            int64_t ip = FACE3(P->poin_in_bdy_face, iface, i, j) - 1;
+            for (int ieq = 0; ieq < q; ++ieq) W->S_flux[ip + N * ieq] += W->S_face[iface + nf * (i + n * (j + n * (int64_t)ieq))];
+        }
+    for (size_t t = 0; t < (size_t)N * q; ++t) RHS[t] = RHS[t] + W->S_flux[t];
+}
+
 /*
  * rhs.jl:498-690  _build_rhs!  steps 1-11 (everything up to, not including, DSS_global_RHS!):
  * zero-fill, u2uaux!, Dirichlet BC (mutates u), inviscid element loop, local DSS, AV viscous
@@ -1013,6 +1154,7 @@ void jxo_build_rhs_local(const jxo_problem *P, double *u, double *RHS, double ti
         DSS_rhs(P, W.RHS_visc, W.rhs_diff_el);                      /* rhs.jl:671 */
         for (size_t t = 0; t < (size_t)N * q; ++t) RHS[t] = RHS[t] + W.RHS_visc[t];   /* rhs.jl:672 */
     }
+    if (P->lbdy_fluxes && P->nsd == 3) apply_boundary_conditions_neumann_3d(P, &W, RHS);   /* rhs.jl:674-689 */
 }
 
 /* element_matrices.jl:972-978 divide_by_mass_matrix! for every equation (rhs.jl:698-699) */

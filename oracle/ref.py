@@ -75,7 +75,10 @@ class _Problem(ctypes.Structure):
                 ("xmin", ctypes.c_double), ("xmax", ctypes.c_double), ("ymin", ctypes.c_double),
                 ("ymax", ctypes.c_double), ("zmin", ctypes.c_double), ("zmax", ctypes.c_double),
                 ("visc_model", ctypes.c_int32), ("lrichardson", ctypes.c_int32), ("ltheta_eqn", ctypes.c_int32),
-                ("sgs_pad", ctypes.c_int32), ("sgs", ctypes.c_double * 8), ("ad_lvl", ctypes.c_void_p)]
+                ("sgs_pad", ctypes.c_int32), ("sgs", ctypes.c_double * 8), ("ad_lvl", ctypes.c_void_p),
+                ("lbdy_fluxes", ctypes.c_int32), ("ifirst_wall_node", ctypes.c_int32),
+                ("delta_hf", ctypes.c_double), ("user_heatflux", ctypes.c_double), ("most", ctypes.c_double * 4),
+                ("bdy_face_in_elem", ctypes.c_void_p), ("Jef", ctypes.c_void_p), ("face_flux_kind", ctypes.c_void_p)]
 
 
 def _f64(a):
@@ -98,9 +101,11 @@ class RefProblem:
     """One rank's `params` as the oracle sees it.  Holds numpy arrays alive for the C struct."""
 
     def __init__(self, sem, qe, *, eq_id=0, lpert=False, lsource=True, lvisc=False, visc_coeff=None,
-                 phys=None, pow_mode=0, neqs=None, sgs=None):
+                 phys=None, pow_mode=0, neqs=None, sgs=None, bdy_fluxes=None):
         """sgs: None (AV) or a dict(model="SMAG"|"VREM", delta=mesh.Δeffective_l, lrichardson=True, ltheta_eqn=True,
-        consts=[Pr_t, Sc_t, mu_mol, kappa_mol, Ri_crit, C_s], ad_lvl=None) -- the SGS struct of sgsStructs.jl."""
+        consts=[Pr_t, Sc_t, mu_mol, kappa_mol, Ri_crit, C_s], ad_lvl=None) -- the SGS struct of sgsStructs.jl.
+        bdy_fluxes: None or a dict(Jef=[nfb,n,n], ifirst_wall_node_index=.., delta_hf=.., user_heatflux=.., karman=0.4,
+        z0_m=0.1, z0_h=0.01) -- inputs[:bdy_fluxes] with the MOST wall model on the faces tagged "MOST" (BCs.jl:655-816)."""
         m = sem.mesh
         self.sem = sem
         self.neqs = neqs if neqs is not None else m.nsd + 2
@@ -152,6 +157,20 @@ class RefProblem:
                 keep["ad_lvl"] = _i64(sgs["ad_lvl"])
                 assert keep["ad_lvl"].shape == (m.nelem,)
                 P.ad_lvl = keep["ad_lvl"].ctypes.data
+        P.lbdy_fluxes = 0
+        if bdy_fluxes is not None:
+            assert m.nsd == 3
+            P.lbdy_fluxes = 1
+            P.ifirst_wall_node = int(bdy_fluxes["ifirst_wall_node_index"])
+            assert 2 <= P.ifirst_wall_node <= m.ngl
+            P.delta_hf, P.user_heatflux = float(bdy_fluxes.get("delta_hf", 0.0)), float(bdy_fluxes.get("user_heatflux", 0.0))
+            P.most[0], P.most[1], P.most[2] = (float(bdy_fluxes.get("karman", 0.4)), float(bdy_fluxes.get("z0_m", 0.1)),
+                                               float(bdy_fluxes.get("z0_h", 0.01)))
+            keep["bfe"] = _i64(m.bdy_face_in_elem)
+            keep["Jef"] = _f64(bdy_fluxes["Jef"])
+            assert keep["Jef"].shape == keep["pibf"].shape
+            keep["fkind"] = np.array([1 if t == "MOST" else 0 for t in m.bdy_face_type], np.int32)
+            P.bdy_face_in_elem, P.Jef, P.face_flux_kind = keep["bfe"].ctypes.data, keep["Jef"].ctypes.data, keep["fkind"].ctypes.data
         assert lib().jxo_sizeof_problem() == ctypes.sizeof(_Problem)
         self.work = np.empty(lib().jxo_work_doubles(ctypes.byref(P)), np.float64)
 

@@ -35,8 +35,8 @@ def params_fields():
 def inputs_keys():
     keys = set()
     for p in ("src/io/mod_inputs.jl", "src/run.jl"):
-        keys |= set(re.findall(r"inputs\[:([A-Za-z_Δμ][A-Za-z0-9_Δμ]*)\]\s*=", read(p)))
-        keys |= set(re.findall(r"haskey\(inputs,\s*:([A-Za-z_Δμ][A-Za-z0-9_Δμ]*)\)", read(p)))
+        keys |= set(re.findall(r"inputs\[:([A-Za-z_Δμδ][A-Za-z0-9_Δμδ]*)\]\s*=", read(p)))
+        keys |= set(re.findall(r"haskey\(inputs,\s*:([A-Za-z_Δμδ][A-Za-z0-9_Δμδ]*)\)", read(p)))
     return sorted(keys)
 
 
@@ -46,7 +46,7 @@ def struct_fields(path, struct):
     names = set()
     for line in m.group(1).split("\n"):
         line = line.split("#")[0].strip()
-        mm = re.match(r"([A-Za-zξηζψωγμκενρλΔ_][\wξηζψωγμκενρλΔ]*)\s*(::|=)", line)
+        mm = re.match(r"([A-Za-zξηζψωγμκενρλδΔ_][\wξηζψωγμκενρλδΔ]*)\s*(::|=)", line)
         if mm:
             names.add(mm.group(1))
     return sorted(names)

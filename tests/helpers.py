@@ -53,3 +53,29 @@ def soliwave_case(nel=(25, 30)):
               "ode_solver": "SSPRK54"}
     u0 = np.ascontiguousarray(qn[:, :3].reshape(-1, order="F"))
     return sems[0], qn, qe, u0, swe_packed(), inputs
+
+
+def most_spec(nel=(3, 2, 3), nop=4, warp=0.05):
+    """A box whose ymin side is the MOST wall, listed in the element's own (i, j) order (BoxSpec.wall_aligned)."""
+    return BoxSpec(nsd=3, nel=tuple(nel), nop=nop, lo=(0.0, 0.0, 0.0), hi=(3000.0, 100.0, 3000.0), periodic=(True, False, False),
+                   tags={"ymin": "MOST"}, warp=warp, wall_aligned=("ymin",))
+
+
+def most_case(lpert, seed=1234):
+    spec = most_spec()
+    sems, qns, qes, us = euler_case(spec, 1, lpert=lpert, seed=seed, vel_amp=6.0)
+    sem = sems[0]
+    m = sem.mesh
+    N = m.npoin
+    u0 = us[0]
+    # a stably and an unstably stratified half of the wall: warm the air over x < L/2, cool it over x > L/2 (theta only)
+    q = u0.reshape(5, N)
+    dth = np.where(m.x < 1500.0, 1.5, -0.05) * np.exp(-m.y / 40.0)
+    rho = q[0] + (qes[0][:, 0] if lpert else 0.0)
+    q[4] += rho * dth
+    q[1] += rho * 8.0          # a mean wind along the wall: the fixed-point iteration for (u*, theta*) converges at every node
+    from jexpresso_b200.sem.metrics import boundary_face_jacobian
+    Jef = boundary_face_jacobian(m, sem.basis)
+    return sem, qes[0], u0, Jef
+
+

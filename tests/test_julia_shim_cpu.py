@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHIM = open(os.path.join(ROOT, "julia", "rhs_b200.jl"), encoding="utf-8").read()
 NAMES = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_names.json"), encoding="utf-8"))
 CODE = "\n".join(line.split("#")[0] for line in SHIM.split("\n"))      # comments stripped
-ID = r"[A-Za-zξηζψωγμκενρλΔ_][\wξηζψωγμκενρλΔ]*"
+ID = r"[A-Za-zξηζψωγμκενρλδΔ_][\wξηζψωγμκενρλδΔ]*"
 
 
 def test_params_fields_exist_in_reference():
