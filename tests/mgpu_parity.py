@@ -31,27 +31,38 @@ def main():
     cases = (((True, True, False), True, 0, 0, (6, 4, 3), 0), ((False, False, False), False, 0, 9, (6, 4, 3), 0),
              ((True, True, False), False, 1, 9, (6, 4, 3), 0), ((False, False, False), False, 1, 9, (12, 12, 3), 2),
              # BASELINE configs[3] at its stated size (64 x 64 x 24 elements, periodic x,y, AV): opt-in, JX_MGPU_CASES=4,5
-             ((True, True, False), True, 0, 0, (64, 64, 24), 0), ((True, True, False), True, 1, 0, (64, 64, 24), 4))
+             ((True, True, False), True, 0, 0, (64, 64, 24), 0), ((True, True, False), True, 1, 0, (64, 64, 24), 4),
+             # Vreman closure (jx_set_sgs; the shipped default of problems/CompEuler/3d) across rank interfaces: bit-exact
+             ((True, True, False), "VREM", 0, 0, (6, 4, 3), 0))
     pick = os.environ.get("JX_MGPU_CASES")
-    pick = {int(x) for x in pick.split(",")} if pick else set(range(4))
+    pick = {int(x) for x in pick.split(",")} if pick else (set(range(4)) | {6})
     for ci, (periodic, lvisc, dss, variant, nel, overlap) in enumerate(cases):
         if ci not in pick:
             continue
+        visc_model = lvisc if isinstance(lvisc, str) else "AV"
+        lvisc = bool(lvisc)
         box = [capi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         big = nel[0] * nel[1] * nel[2] > 10000
         nsteps = 1 if big else 3
         spec = box3d(nel, 4, warp=0.05, periodic=periodic, L=(10000.0, 10000.0, 3750.0)) if big else box3d(nel, 4, warp=0.05, periodic=periodic)
         sems, qns, qes, us = euler_case(spec, world, lpert=False)
-        probs = [ref.RefProblem(s, qe, eq_id=0, lpert=False, lsource=True, lvisc=lvisc, visc_coeff=MU3, phys=PHYS, pow_mode=1)
+        mu = MU3 if visc_model == "AV" else [0.0, 1.0, 1.0, 1.0, 2.0]
+        sgs, delta = None, None
+        if visc_model != "AV":
+            from jexpresso_b200.physics import PhysicalConst
+            from jexpresso_b200.sem import effective_delta_l
+            delta = effective_delta_l([s.mesh for s in sems])           # mesh.Δeffective_l: the maximum over all ranks
+            sgs = dict(model=visc_model, delta=delta, lrichardson=True, ltheta_eqn=True, consts=PhysicalConst().sgs_packed())
+        probs = [ref.RefProblem(s, qe, eq_id=0, lpert=False, lsource=True, lvisc=lvisc, visc_coeff=mu, phys=PHYS, pow_mode=1, sgs=sgs)
                  for s, qe in zip(sems, qes)]
         caches = ref.setup_assembler([s.mesh.ip2gip for s in sems], [s.mesh.gip2owner for s in sems])
         run = ref.RefRun(probs, caches)
         uo = [u.copy() for u in us]
         duo = [np.zeros_like(u) for u in us]
         run.rhs(duo, uo, 0.0)
-        inputs = {"SOL_VARS_TYPE": "TOTAL", "lsource": True, "lvisc": lvisc, "mu": MU3, "dt": 0.05 if big else 0.4,   # 39 m node spacing at C4
-                  "ode_solver": "CarpenterKennedy2N54"}
+        inputs = {"SOL_VARS_TYPE": "TOTAL", "lsource": True, "lvisc": lvisc, "mu": mu, "dt": 0.05 if big else 0.4,   # 39 m node spacing at C4
+                  "ode_solver": "CarpenterKennedy2N54", "visc_model": visc_model, "delta_effective": delta}
         p = jrhs.params_setup(sems[rank], qes[rank], inputs, device=local, rank=rank, nranks=world, nccl_uid=box[0],
                               pow_mode=1, dss_mode=dss, elem_kernel=variant, overlap=overlap)
         split = p.ctx.split_info()
@@ -74,7 +85,7 @@ def main():
         if overlap and world <= 4:          # (with more ranks the small box has no interior pairs left: nothing to split)
             good = good and split[0] > 0 and split[1] > 0
         ok &= good
-        print(f"[rank {rank}/{world}] nel={nel} periodic={periodic} visc={lvisc} dss={dss} kernel={variant} overlap={overlap} split={split}: rhs pn={pn:.2e} l2={l2:.2e} "
+        print(f"[rank {rank}/{world}] nel={nel} periodic={periodic} visc={visc_model if lvisc else False} dss={dss} kernel={variant} overlap={overlap} split={split}: rhs pn={pn:.2e} l2={l2:.2e} "
               f"{nsteps} steps pn={pn2:.2e} l2={l22:.2e} bit_exact={exact} -> {'OK' if good else 'FAIL'}", flush=True)
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
