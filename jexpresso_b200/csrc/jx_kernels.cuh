@@ -1048,11 +1048,22 @@ k_elem_team(const __grid_constant__ ElemArgs a) {
 #if JX_TEAM_L2PF
             // everything this launch reads of the record except the flux-view ids (loaded above): the plane and zeta rows,
             // ONE of the two weight blocks, the zeta-view ids -- two contiguous ranges
-            constexpr int CH = 1024;
+            // The instruction runs on the uniform datapath, lane by lane: 22 one-kilobyte chunks issued by the first lanes of
+            // warp 0 made that warp the last to reach the group barrier, with the three others waiting for it (8 % of all warp
+            // samples, profiles/r02h_team_source_stalls.md).  Now lane 0 of every warp pulls an equal slice of the first
+            // range and lane 1 of the last warp the second: NW + 1 bulk prefetches per group, spread over the warps.
             constexpr int A_END = fold ? C::W_OFF : C::WF_OFF, B_BEG = fold ? C::WF_OFF : C::ZID_OFF;
+            constexpr int NW = NT / 32;
+            constexpr int SL = ((A_END + NW - 1) / NW + 15) / 16 * 16;
             const char *rn = a.rec + (size_t)gn * C::GROUP_BYTES;
-            for (int off = t * CH; off < A_END; off += NT * CH) prefetch_l2_bulk(rn + off, (A_END - off) < CH ? (A_END - off) : CH);
-            for (int off = B_BEG + t * CH; off < C::FID_OFF; off += NT * CH) prefetch_l2_bulk(rn + off, (C::FID_OFF - off) < CH ? (C::FID_OFF - off) : CH);
+            const int w = t >> 5;
+            if (lane == 0) {
+                const int off = w * SL;
+                const int sz = ((A_END - off) < SL ? (A_END - off) : SL) & ~15;
+                if (sz > 0) prefetch_l2_bulk(rn + off, (uint32_t)sz);
+            } else if (lane == 1 && w == NW - 1) {
+                prefetch_l2_bulk(rn + B_BEG, (uint32_t)((C::FID_OFF - B_BEG) & ~15));
+            }
 #endif
         }
     };

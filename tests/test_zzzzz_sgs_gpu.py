@@ -32,8 +32,8 @@ def _oracle(sem, qe, inputs, neqs, eq_id=0, phys=PHYS):
                           visc_coeff=np.array(inputs["mu"], float), phys=phys, pow_mode=1, neqs=neqs, sgs=sgs)
 
 
-def _one_rhs(sem, qe, u0, inputs, neqs, eqs="CompEuler", eq_id=0, phys=PHYS, dss_mode=0):
-    run = ref.RefRun([_oracle(sem, qe, inputs, neqs, eq_id, phys)])
+def _one_rhs(sem, qe, u0, inputs, neqs, eqs="CompEuler", eq_id=0, phys=PHYS, dss_mode=0, caches=None):
+    run = ref.RefRun([_oracle(sem, qe, inputs, neqs, eq_id, phys)], caches)
     uo, duo = [u0.copy()], [np.zeros_like(u0)]
     run.rhs(duo, uo, 0.0)
     p = jrhs.params_setup(sem, qe, inputs, eqs=eqs, phys=phys, pow_mode=1, dss_mode=dss_mode)
@@ -162,6 +162,21 @@ def test_sgs_atomics_mode_and_steps():
     finally:
         p.close()
     assert np.array_equal(ug, uo[0]), float(np.max(np.abs(ug - uo[0])))
+
+
+def test_sgs_c4_abl_box_vrem_at_stated_size():
+    """BASELINE configs[3] -- the turbulent ABL-style box, 64 x 64 x 24 elements, nop 4, periodic in x and y -- with the Vreman
+    closure (the shipped default of problems/CompEuler/3d/user_inputs.jl:33) at its stated size: one rhs!, bit-exact against
+    the oracle (which needs about half a minute per evaluation here).  JX_C4_NEL shrinks it for quick runs."""
+    import os
+    nel = tuple(int(x) for x in os.environ.get("JX_C4_NEL", "64,64,24").split(","))
+    spec = box3d(nel, 4, warp=0.05, periodic=(True, True, False), L=(10000.0, 10000.0, 3750.0))
+    sems, qns, qes, us = euler_case(spec, 1, lpert=False)
+    m = sems[0].mesh
+    inputs = _inputs("VREM", MU_SGS3, False, delta=effective_delta_l(m))
+    du, want = _one_rhs(sems[0], qes[0], us[0], inputs, 5, caches=ref.setup_assembler([m.ip2gip], [m.gip2owner]))
+    assert np.isfinite(du).all()
+    assert np.array_equal(du, want), rel_err_per_node(du, want)
 
 
 def test_sgs_refused_configurations():
