@@ -30,7 +30,9 @@
  * 1e-9; wet/dry-front nodes up to 5e-6).  PARITY UNPINNED: the total-energy functor (the reference holds no
  * golden vector for kelvinHelmholtzChan2022; its flux, primitives (ρ,u,v,T) and τ·u term are restated from
  * user_flux.jl:30-48, user_primitives.jl:17-23 and rhs.jl:1988, 2018-2041 and checked against an independent
- * numpy transcription in tests/test_energy_functor_cpu.py).
+ * numpy transcription in tests/test_energy_functor_cpu.py); the SGS closures (SMAG / VREM; SGS.jl, rhs.jl:2275-2400, 2582-2785) and the
+ * boundary fluxes with the Monin-Obukhov wall model (BCs.jl:655-816, CM_MOST.jl, surface_integral.jl) -- no deck with them has a
+ * golden vector; both are checked against independent numpy transcriptions (tests/test_sgs_cpu.py, tests/test_bdy_flux_cpu.py).
  */
 #include <math.h>
 #include <stdint.h>
