@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["assemble_dist", "host_group"]
+__all__ = ["assemble_dist", "host_group", "effective_delta_dist"]
 
 _HOST_GROUP = None
 
@@ -76,3 +76,15 @@ def assemble_dist(a, lists, group=None):
     for r, buf in got.items():
         a2[lists.recvback_idx[r] - 1, :] = buf
     return a
+
+
+def effective_delta_dist(mesh, group=None):
+    """mesh.Δeffective_l of a partitioned mesh: compute_element_size_driver takes MPI.Allreduce(maximum(Δelem), MAX) before it
+    divides by nop (src/kernel/mesh/mesh.jl:5621-5632) -- every rank must hand the same value to jx_set_sgs."""
+    import torch
+    import torch.distributed as dist
+    from .sem.mesh import element_sizes
+    t = torch.tensor([float(element_sizes(mesh).max())], dtype=torch.float64)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group if group is not None else host_group())
+    return float(t.item()) / mesh.nop

@@ -50,7 +50,9 @@ def _worker(rank, world, port, q):
         sem = sem_setup_rank(spec, rank, world)
         qn, qe = rtb_initial_state(sem.mesh, False, seed=7)
         conformity4ncf_q_rank(sem, qn, 5)
-        q.put((rank, sem.M.copy(), sem.Minv.copy(), sem.nx.copy(), sem.nz.copy(), qn.copy(), sem.mesh.gip2owner.copy()))
+        from jexpresso_b200.distributed import effective_delta_dist
+        q.put((rank, sem.M.copy(), sem.Minv.copy(), sem.nx.copy(), sem.nz.copy(), qn.copy(), sem.mesh.gip2owner.copy(),
+               effective_delta_dist(sem.mesh)))
     finally:
         dist.destroy_process_group()
 
@@ -74,7 +76,9 @@ def test_gloo_world2_setup_matches_literal():
     spec = box3d((4, 4, 2), 3, warp=0.04)
     sems, qns, qes, us = euler_case(spec, world, lpert=False, seed=7)
     for r in range(world):
-        M, Minv, nx, nz, qn, owner = got[r]
+        M, Minv, nx, nz, qn, owner, delta = got[r]
+        from jexpresso_b200.sem import effective_delta_l
+        assert delta == effective_delta_l([x.mesh for x in sems])      # the Allreduce(MAX) of mesh.jl:5629-5632: one value on all ranks
         assert np.array_equal(owner, sems[r].mesh.gip2owner)
         assert np.array_equal(M, sems[r].M) and np.array_equal(Minv, sems[r].Minv)
         assert np.array_equal(nx, sems[r].nx) and np.array_equal(nz, sems[r].nz)
