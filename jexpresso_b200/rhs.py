@@ -86,7 +86,12 @@ def params_setup(sem, qe, inputs, *, device=0, rank=0, nranks=1, nccl_uid=None, 
             # params.sgs = allocate_SGS(...) with the flags of params_setup.jl:249-253.  mesh.Δeffective_l is a global maximum
             # (mesh.jl:5629-5632): multi-rank callers pass it as inputs["delta_effective"]
             from .sem import effective_delta_l
-            delta = inputs.get("delta_effective") or effective_delta_l(m)
+            delta = inputs.get("delta_effective")
+            if not delta:
+                if nranks > 1:
+                    raise ValueError("visc_model SMAG/VREM on several ranks: pass the GLOBAL mesh.Δeffective_l as "
+                                     "inputs['delta_effective'] (jexpresso_b200.distributed.effective_delta_dist)")
+                delta = effective_delta_l(m)
             ctx.set_sgs(visc_model, delta, inputs.get("lrichardson", True), inputs.get("energy_equation", "theta") != "energy",
                         inputs.get("sgs_consts") or PhysicalConst().sgs_packed(), inputs.get("ad_lvl"))
         if device_metrics or device_mass:   # build_metric_terms! on the device (jx_upload_mesh_coords): sem.metrics is not read;

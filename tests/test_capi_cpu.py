@@ -49,3 +49,27 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 for needle in ("import oracle", "from oracle", "libjexref", "jexref.c\"", "oracle/_build", "oracle/_ref"):
                     assert needle not in txt, (f, needle)
+
+
+def test_params_setup_refuses_a_rank_local_effective_delta():
+    """mesh.Δeffective_l is a maximum over ALL ranks (mesh.jl:5629-5632); a closure run on several ranks must be handed that value,
+    never this rank's own -- checked before anything touches the GPU."""
+    import pytest
+    from jexpresso_b200 import rhs as jrhs
+    from jexpresso_b200.sem.problems import box3d, euler_case
+    sems, qns, qes, us = euler_case(box3d((4, 2, 2), 2), 2, lpert=False)
+    inputs = {"SOL_VARS_TYPE": "TOTAL", "lsource": True, "lvisc": True, "mu": [0.0, 1.0, 1.0, 1.0, 2.0], "visc_model": "VREM"}
+
+    class _Ctx:                      # stands in for capi.Context up to the point of the check
+        def __init__(self, *a, **k): pass
+        def set_option(self, *a): pass
+        def set_problem(self, *a): pass
+        def close(self): pass
+
+    real = jrhs.capi.Context
+    jrhs.capi.Context = _Ctx
+    try:
+        with pytest.raises(ValueError, match="GLOBAL"):
+            jrhs.params_setup(sems[0], qes[0], inputs, rank=0, nranks=2, nccl_uid=b"\0" * 128)
+    finally:
+        jrhs.capi.Context = real
